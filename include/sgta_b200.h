@@ -1,0 +1,152 @@
+/*
+ * sgta_b200.h -- C ABI of libsgta_b200.so: the B200 (sm_100a) hot path of SGTAPose's
+ * per-frame dense inference.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (the Python host passes torch allocator pointers), unless marked HOST;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) and never synchronise;
+ *   - return 0 on success, a negative SGTA_E* code otherwise; nothing throws across the
+ *     ABI; sgta_last_error() returns a HOST string describing the last failure of the
+ *     calling thread.
+ *
+ * Each entry point names the reference interface it replaces (file:line in
+ * Nimolty/SGTAPose; the DCNv2 extension itself is third party).
+ */
+#ifndef SGTA_B200_H_
+#define SGTA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGTA_OK 0
+#define SGTA_EINVAL (-1)      /* bad argument / unsupported shape            */
+#define SGTA_ECUDA (-2)       /* CUDA runtime error at launch                */
+#define SGTA_EUNSUPPORTED (-3) /* valid call, but no kernel for this config   */
+
+#define SGTA_DTYPE_F32 0
+#define SGTA_DTYPE_BF16 1
+
+int sgta_abi_version(void);
+const char* sgta_last_error(void);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+int64_t sgta_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * DCNv2 forward, reference layout.  Replaces `_ext.dcn_v2_forward` of lbin/DCNv2 as
+ * reached from `DCN.forward`, constructed at sgtapose/lib/model/networks/dla.py:545 and
+ * called at dla.py:548.
+ *   x            [B, Cin, H, W]              fp32 NCHW
+ *   offset_mask  [B, 3*dg*kh*kw, Ho, Wo]     RAW output of conv_offset_mask: first
+ *                2*dg*kh*kw channels are (dy,dx) interleaved per tap, the rest are mask
+ *                logits; the sigmoid is applied inside the kernel
+ *   weight       [Cout, Cin, kh, kw], bias [Cout] (may be NULL)
+ *   y            [B, Cout, Ho, Wo]           fp32 NCHW
+ * dtype must be SGTA_DTYPE_F32 (exact fp32 FMA arithmetic, CUDA cores).
+ * --------------------------------------------------------------------------------- */
+int sgta_dcn_forward(const void* x, const void* offset_mask, const void* weight,
+                     const void* bias, void* y, int B, int Cin, int Cout, int H, int W,
+                     int kh, int kw, int stride, int pad, int dil, int dgroups, int dtype,
+                     void* stream);
+
+/* DCNv2 backward (training config 5).  Replaces `_ext.dcn_v2_backward`.
+ * grad_offset_mask is w.r.t. the RAW conv_offset_mask output (sigmoid' folded in).
+ * grad_* buffers are OVERWRITTEN, except grad_weight / grad_bias which are accumulated
+ * into (caller zero-fills).  Any grad_* may be NULL to skip it. */
+int sgta_dcn_backward(const void* x, const void* offset_mask, const void* weight,
+                      const void* grad_y, void* grad_x, void* grad_offset_mask,
+                      void* grad_weight, void* grad_bias, int B, int Cin, int Cout, int H,
+                      int W, int kh, int kw, int stride, int pad, int dil, int dgroups,
+                      int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * DCNv2 forward, B200 fast path: NHWC activations, implicit GEMM on tcgen05/TMEM.
+ * 3x3, stride 1, pad 1, dil 1, dg 1 (the only configuration dla.py:545 constructs),
+ * Cin % 64 == 0, Cout % 16 == 0, 16 <= Cout <= 256.
+ *   x            [B, H, W, Cin]   fp32 (mode F32X3) or bf16 (mode BF16)
+ *   offset_mask  [B, H, W, 32]    fp32 raw conv_offset_mask output, channels 0..26 used
+ *   wpack        weights pre-packed by sgta_dcn_pack_weight (UMMA smem image, per K block)
+ *   scale, shift [Cout] fp32: y = relu?(acc * scale + shift)   (bias + eval-BN folded)
+ *   y            [B, H, W, Cout]  fp32 or bf16 (out_dtype)
+ * mode: 0 = BF16 operands / fp32 accumulate; 1 = F32X3 (hi/lo bf16 split of both
+ * operands, three MMAs per tile: ~2^-16 relative, used for the fp32 parity bound).
+ * --------------------------------------------------------------------------------- */
+#define SGTA_MMA_BF16 0
+#define SGTA_MMA_F32X3 1
+int64_t sgta_dcn_wpack_bytes(int Cin, int Cout, int mode);
+int sgta_dcn_pack_weight(const void* weight_f32 /*[Cout,Cin,3,3]*/, void* wpack, int Cin,
+                         int Cout, int mode, void* stream);
+int sgta_dcn_forward_nhwc(const void* x, const void* offset_mask, const void* wpack,
+                          const void* scale, const void* shift, void* y, int B, int Cin,
+                          int Cout, int H, int W, int mode, int relu, int out_dtype,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Structure-prior temporal attention (dla.py:868-887 MHCA_ein.forward core):
+ *   out[b,i,h,:] = softmax_j( q[b,i,h,:].k[b,j,h,:] * inv_scale + pos[h,i,j] ) v[b,j,h,:]
+ * q [B,nq,heads*d], k,v [B,nk,heads*d], out [B,nq,heads*d] fp32, "b n (h d)" layout (the
+ * Linear outputs as they are, no rearrange); pos [heads,nq,nk] fp32 or NULL.
+ * d in {4, 8, 16, 32}.
+ * --------------------------------------------------------------------------------- */
+int sgta_attn_forward(const void* q, const void* k, const void* v, const void* pos,
+                      void* out, int B, int heads, int nq, int nk, int d, float inv_scale,
+                      void* stream);
+/* backward of the same core (config 5): grads w.r.t. q, k, v, pos (pos grad accumulated) */
+int sgta_attn_backward(const void* q, const void* k, const void* v, const void* pos,
+                       const void* grad_out, void* grad_q, void* grad_k, void* grad_v,
+                       void* grad_pos, int B, int heads, int nq, int nk, int d,
+                       float inv_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Prior-guided token selection (dla.py:898-913 get_topk_index, :915-968
+ * get_topk_features_scale, :1006-1018 substitute_topk_features_scale).
+ * --------------------------------------------------------------------------------- */
+/* top-K flat index per (sample, channel); ties: value descending, lowest index first.
+ * hm [B,C,HW] fp32 -> idx [B, C*K] int64 */
+int sgta_topk_index(const void* hm, void* idx, int B, int C, int HW, int K, void* stream);
+/* window ids with the reference's fp32 index arithmetic:
+ * idx [B,CK] int64 (flat index in a Whm-wide map) -> ids [B, CK*win*win] int64,
+ * win = 2*(kernel/2)+1, coords = (x,y)*scale + offset, clamp [0,H-1], id = y*W + x (fp32),
+ * truncated. */
+int sgta_window_ids(const void* idx, void* ids, int B, int CK, int Whm, float scale,
+                    int kernel, int H, int W, void* stream);
+/* rows[b,t,:] = feats[b,:,ids[b,t]]   (feats NCHW fp32 if nhwc==0 else NHWC) */
+int sgta_gather_tokens(const void* feats, const void* ids, void* rows, int B, int C, int HW,
+                       int n, int nhwc, void* stream);
+/* feats[b,:,ids[b,t]] = rows[b,t,:]; duplicate ids: the HIGHEST t wins (deterministic). */
+int sgta_scatter_tokens(void* feats, const void* ids, const void* rows, int B, int C, int HW,
+                        int n, int nhwc, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Heatmap decode.
+ * --------------------------------------------------------------------------------- */
+/* Live decode: dream_generic_decode -> _peaks_info -> peaks_from_belief_maps
+ * (sgtapose/lib/model/decode.py:184-313, lib/model/utils.py:207-284,
+ *  sgtapose/image_proc.py:1032-1143), one keypoint per channel, every sample decoded.
+ *   hm [B,C,h,w] fp32 (post-sigmoid), reg [B,2,h,w] or NULL, tracking [B,2,h,w] or NULL
+ *   scores [B,C] f32 (-1 = missing), inds/xs/ys [B,C] int64,
+ *   cts_wreg [B,C,2] f32 (x_int + reg_x, y_int + reg_y; +0.5 if reg NULL),
+ *   trk [B,C,2] f32 (ignored if tracking NULL)
+ * gauss_w: HOST pointer to the 25 float64 blur taps (scipy _gaussian_kernel1d(3,0,12));
+ * integer outputs are bit-exact w.r.t. scipy/numpy double arithmetic. */
+int sgta_decode_peaks(const void* hm, const void* reg, const void* tracking, void* scores,
+                      void* inds, void* xs, void* ys, void* cts_wreg, void* trk,
+                      const double* gauss_w, int B, int C, int h, int w, void* stream);
+/* Alternate decode: _nms + _topk (lib/model/utils.py:59-103; generic_decode decode.py:93-94).
+ *   scores [B,K] f32, inds [B,K] int64, clses [B,K] int32; workspace >= B*C*K*12 bytes */
+int sgta_decode_nms_topk(const void* hm, void* scores, void* inds, void* clses,
+                         void* workspace, int B, int C, int h, int w, int K, void* stream);
+/* 3x3 max-pool NMS alone (utils.py:59-65): out = hm * (maxpool3x3(hm) == hm) */
+int sgta_nms3x3(const void* hm, void* out, int B, int C, int h, int w, void* stream);
+/* SoftArgmaxPavlo.forward (sgtapose/spatial_softmax.py:24-95): out [B,C,2] = (E[x], E[y]) */
+int sgta_soft_argmax(const void* hm, void* out, int B, int C, int h, int w, float beta,
+                     float size_mult, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGTA_B200_H_ */

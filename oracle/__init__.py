@@ -1,0 +1,17 @@
+"""CPU oracle for the SGTAPose per-frame dense inference path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it, and there only as the checker (or as
+the thing timed on the host cores), never on the CUDA product path.
+
+Every function cites the reference file:line it restates.  Parity pinning:
+the reference ships no tests or golden vectors, so the
+oracle is pinned against outputs of the reference's own Python, imported from
+``/root/reference`` in the build container by ``oracle/make_golden.py`` and
+committed under ``tests/golden/``.  The one exception is the DCNv2 operator
+itself: its arithmetic lives in the un-vendored third-party extension
+lbin/DCNv2 (branch ``pytorch_<ver>``, no pinned commit, README.md:21-28), so at
+that single boundary parity is pinned to ``torchvision.ops.deform_conv2d``
+(the CPU stand-in BASELINE.json names), not to upstream DCNv2 sources.
+"""

@@ -1,0 +1,90 @@
+"""ctypes binding of libsgta_b200.so (the C ABI declared in include/sgta_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or a kernel call
+fails, this module raises.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsgta_b200.so")
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_F = _c.c_float
+
+# name -> (restype, argtypes); mirrors include/sgta_b200.h one to one
+SIGNATURES = {
+    "sgta_abi_version": (_I, []),
+    "sgta_last_error": (_c.c_char_p, []),
+    "sgta_launch_count": (_c.c_int64, []),
+    "sgta_dcn_forward": (_I, [_P] * 5 + [_I] * 12 + [_P]),
+    "sgta_dcn_backward": (_I, [_P] * 8 + [_I] * 12 + [_P]),
+    "sgta_dcn_wpack_bytes": (_c.c_int64, [_I, _I, _I]),
+    "sgta_dcn_pack_weight": (_I, [_P, _P, _I, _I, _I, _P]),
+    "sgta_dcn_forward_nhwc": (_I, [_P] * 6 + [_I] * 8 + [_P]),
+    "sgta_attn_forward": (_I, [_P] * 5 + [_I] * 5 + [_F, _P]),
+    "sgta_attn_backward": (_I, [_P] * 9 + [_I] * 5 + [_F, _P]),
+    "sgta_topk_index": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "sgta_window_ids": (_I, [_P, _P, _I, _I, _I, _F, _I, _I, _I, _P]),
+    "sgta_gather_tokens": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "sgta_scatter_tokens": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "sgta_decode_peaks": (_I, [_P] * 9 + [_c.POINTER(_c.c_double)] + [_I] * 4 + [_P]),
+    "sgta_decode_nms_topk": (_I, [_P] * 5 + [_I] * 5 + [_P]),
+    "sgta_nms3x3": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "sgta_soft_argmax": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
+}
+
+_lib = None
+
+
+class SgtaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SgtaError(
+            "libsgta_b200.so not found at %s -- build it with `python -m sgtapose_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise SgtaError with the library's message."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise SgtaError("%s failed (%d): %s" % (name, rc, lib.sgta_last_error().decode()))
+
+
+def launch_count():
+    return int(load().sgta_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SgtaError("expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise SgtaError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,258 @@
+// Structure-prior temporal attention core: fused QK^T/scale + pos_embed -> softmax -> V.
+//
+// Replaces the einsum / softmax / einsum triple of MHCA_ein.forward (reference
+// sgtapose/lib/model/networks/dla.py:878-885), which materialises the [B,8,n,n] energy
+// and attention tensors (45 MB per sample at level 0) in HBM.  Here one warp owns one
+// query row of one head: its 32 lanes stride over the keys with an online softmax
+// (running max / sum in the log2 domain), K and V of the (sample, head) live in shared
+// memory, pos_embed rows are read once, coalesced, straight from L2/HBM, and the lane
+// partials are merged with warp-shuffle reductions.  Nothing n x n is ever stored.
+//
+// Layout: q,k,v,out are the Linear outputs as they are, [B, n, heads*d] ("b n (h d)").
+#include "common.cuh"
+
+namespace sgta {
+
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_ROWS = 32;          // query rows per CTA (4 per warp)
+constexpr float LOG2E = 1.4426950408889634f;
+
+template <int D> struct KPad { static constexpr int stride = (D == 4) ? 4 : D + 4; };
+
+template <int D>
+__device__ __forceinline__ void load_row(float (&dst)[D], const float* __restrict__ src) {
+#pragma unroll
+  for (int i = 0; i < D; i += 4) {
+    float4 t = *reinterpret_cast<const float4*>(src + i);
+    dst[i] = t.x; dst[i + 1] = t.y; dst[i + 2] = t.z; dst[i + 3] = t.w;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void stage_kv(float* Ks, float* Vs, const float* __restrict__ kb,
+                                         const float* __restrict__ vb, int nk, int HD, int h) {
+  constexpr int S = KPad<D>::stride;
+  constexpr int V4 = D / 4;
+  for (int e = threadIdx.x; e < nk * V4; e += blockDim.x) {
+    int j = e / V4, c = (e % V4) * 4;
+    float4 kk = __ldg(reinterpret_cast<const float4*>(kb + (long long)j * HD + h * D + c));
+    float4 vv = __ldg(reinterpret_cast<const float4*>(vb + (long long)j * HD + h * D + c));
+    *reinterpret_cast<float4*>(Ks + j * S + c) = kk;
+    *reinterpret_cast<float4*>(Vs + j * S + c) = vv;
+  }
+}
+
+// grid (ceil(nq/ATT_ROWS), heads, B), 256 threads, smem 2*nk*stride floats
+template <int D>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                const float* __restrict__ v, const float* __restrict__ pos,
+                float* __restrict__ out, int heads, int nq, int nk, float inv_scale) {
+  constexpr int S = KPad<D>::stride;
+  extern __shared__ __align__(16) float att_smem[];
+  float* Ks = att_smem;
+  float* Vs = att_smem + (size_t)nk * S;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int HD = heads * D;
+  stage_kv<D>(Ks, Vs, k + (long long)b * nk * HD, v + (long long)b * nk * HD, nk, HD, h);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float sc = inv_scale * LOG2E;
+  for (int r = warp; r < ATT_ROWS; r += ATT_WARPS) {
+    const int i = blockIdx.x * ATT_ROWS + r;
+    if (i >= nq) break;
+    float qr[D];
+    load_row<D>(qr, q + ((long long)b * nq + i) * HD + h * D);
+#pragma unroll
+    for (int c = 0; c < D; ++c) qr[c] *= sc;
+    const float* prow = pos ? pos + ((long long)h * nq + i) * nk : nullptr;
+    float m = -INFINITY, l = 0.f, acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      float kr[D];
+      load_row<D>(kr, Ks + j * S);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) s = fmaf(qr[c], kr[c], s);
+      if (prow) s = fmaf(__ldg(prow + j), LOG2E, s);
+      if (s > m) {
+        float corr = exp2f(m - s);
+        l *= corr;
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] *= corr;
+        m = s;
+      }
+      float p = exp2f(s - m);
+      l += p;
+      float vr[D];
+      load_row<D>(vr, Vs + j * S);
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[c] = fmaf(p, vr[c], acc[c]);
+    }
+    float M = warp_max(m);
+    float f = (m == -INFINITY) ? 0.f : exp2f(m - M);
+    l = warp_sum(l * f);
+    float inv = 1.f / l;
+    float* orow = out + ((long long)b * nq + i) * HD + h * D;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      float a = warp_sum(acc[c] * f);
+      if (lane == c) orow[c] = a * inv;
+    }
+  }
+}
+
+// Backward of the same core.  One warp per query row; recomputes the softmax statistics,
+// then ds_j = p_j (dp_j - delta) with delta = gout_i . out_i.
+//   gq_i = inv_scale * sum_j ds_j k_j          (registers + warp reduce)
+//   gk_j += inv_scale * ds_j q_i, gv_j += p_j gout_i, gpos[h,i,j] += ds_j   (atomicAdd)
+template <int D>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                const float* __restrict__ v, const float* __restrict__ pos,
+                const float* __restrict__ gout, float* __restrict__ gq, float* __restrict__ gk,
+                float* __restrict__ gv, float* __restrict__ gpos, int heads, int nq, int nk,
+                float inv_scale) {
+  constexpr int S = KPad<D>::stride;
+  extern __shared__ __align__(16) float att_smem[];
+  float* Ks = att_smem;
+  float* Vs = att_smem + (size_t)nk * S;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int HD = heads * D;
+  stage_kv<D>(Ks, Vs, k + (long long)b * nk * HD, v + (long long)b * nk * HD, nk, HD, h);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float sc = inv_scale * LOG2E;
+  for (int r = warp; r < ATT_ROWS; r += ATT_WARPS) {
+    const int i = blockIdx.x * ATT_ROWS + r;
+    if (i >= nq) break;
+    float qr[D], go[D];
+    const long long rowoff = ((long long)b * nq + i) * HD + h * D;
+    load_row<D>(qr, q + rowoff);
+    load_row<D>(go, gout + rowoff);
+    const float* prow = pos ? pos + ((long long)h * nq + i) * nk : nullptr;
+    // pass 1: statistics and delta
+    float m = -INFINITY, l = 0.f, dacc = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      float kr[D], vr[D];
+      load_row<D>(kr, Ks + j * S);
+      load_row<D>(vr, Vs + j * S);
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { s = fmaf(qr[c] * sc, kr[c], s); dp = fmaf(go[c], vr[c], dp); }
+      if (prow) s = fmaf(__ldg(prow + j), LOG2E, s);
+      if (s > m) { float corr = exp2f(m - s); l *= corr; dacc *= corr; m = s; }
+      float p = exp2f(s - m);
+      l += p; dacc = fmaf(p, dp, dacc);
+    }
+    float M = warp_max(m);
+    float f = (m == -INFINITY) ? 0.f : exp2f(m - M);
+    float L = warp_sum(l * f);
+    float delta = warp_sum(dacc * f) / L;
+    float invL = 1.f / L;
+    // pass 2
+    float gqa[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) gqa[c] = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      float kr[D], vr[D];
+      load_row<D>(kr, Ks + j * S);
+      load_row<D>(vr, Vs + j * S);
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { s = fmaf(qr[c] * sc, kr[c], s); dp = fmaf(go[c], vr[c], dp); }
+      if (prow) s = fmaf(__ldg(prow + j), LOG2E, s);
+      float p = exp2f(s - M) * invL;
+      float ds = p * (dp - delta);
+      if (gpos) atomicAdd(gpos + ((long long)h * nq + i) * nk + j, ds);
+      float* gkr = gk + ((long long)b * nk + j) * HD + h * D;
+      float* gvr = gv + ((long long)b * nk + j) * HD + h * D;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        gqa[c] = fmaf(ds, kr[c], gqa[c]);
+        atomicAdd(gkr + c, ds * inv_scale * qr[c]);
+        atomicAdd(gvr + c, p * go[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      float a = warp_sum(gqa[c]);
+      if (lane == c) gq[rowoff + c] = a * inv_scale;
+    }
+  }
+}
+
+template <int D>
+static int launch_fwd(const float* q, const float* k, const float* v, const float* pos, float* out,
+                      int B, int heads, int nq, int nk, float inv_scale, cudaStream_t st) {
+  size_t smem = sizeof(float) * 2 * (size_t)nk * KPad<D>::stride;
+  SGTA_REQUIRE(smem <= 220 * 1024, "sgta_attn_forward: nk=%d too large for shared memory", nk);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(cdiv(nq, ATT_ROWS), heads, B);
+  attn_fwd_kernel<D><<<grid, ATT_WARPS * 32, smem, st>>>(q, k, v, pos, out, heads, nq, nk, inv_scale);
+  return check_launch("attn_fwd_kernel");
+}
+
+template <int D>
+static int launch_bwd(const float* q, const float* k, const float* v, const float* pos,
+                      const float* go, float* gq, float* gk, float* gv, float* gpos, int B,
+                      int heads, int nq, int nk, float inv_scale, cudaStream_t st) {
+  size_t smem = sizeof(float) * 2 * (size_t)nk * KPad<D>::stride;
+  SGTA_REQUIRE(smem <= 220 * 1024, "sgta_attn_backward: nk=%d too large for shared memory", nk);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t kvbytes = sizeof(float) * (size_t)B * nk * heads * D;
+  cudaMemsetAsync(gk, 0, kvbytes, st);
+  cudaMemsetAsync(gv, 0, kvbytes, st);
+  dim3 grid(cdiv(nq, ATT_ROWS), heads, B);
+  attn_bwd_kernel<D><<<grid, ATT_WARPS * 32, smem, st>>>(q, k, v, pos, go, gq, gk, gv, gpos, heads,
+                                                        nq, nk, inv_scale);
+  return check_launch("attn_bwd_kernel");
+}
+
+}  // namespace sgta
+
+using namespace sgta;
+
+extern "C" int sgta_attn_forward(const void* q, const void* k, const void* v, const void* pos,
+                                 void* out, int B, int heads, int nq, int nk, int d,
+                                 float inv_scale, void* stream) {
+  SGTA_REQUIRE(q && k && v && out, "sgta_attn_forward: null pointer");
+  SGTA_REQUIRE(B > 0 && B <= 65535 && heads > 0 && heads <= 65535 && nq > 0 && nk > 0,
+               "sgta_attn_forward: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float *Q = (const float*)q, *K = (const float*)k, *V = (const float*)v, *P = (const float*)pos;
+  switch (d) {
+    case 4: return launch_fwd<4>(Q, K, V, P, (float*)out, B, heads, nq, nk, inv_scale, st);
+    case 8: return launch_fwd<8>(Q, K, V, P, (float*)out, B, heads, nq, nk, inv_scale, st);
+    case 16: return launch_fwd<16>(Q, K, V, P, (float*)out, B, heads, nq, nk, inv_scale, st);
+    case 32: return launch_fwd<32>(Q, K, V, P, (float*)out, B, heads, nq, nk, inv_scale, st);
+    default:
+      set_error("sgta_attn_forward: head dim %d not in {4,8,16,32}", d);
+      return SGTA_EUNSUPPORTED;
+  }
+}
+
+extern "C" int sgta_attn_backward(const void* q, const void* k, const void* v, const void* pos,
+                                  const void* grad_out, void* grad_q, void* grad_k, void* grad_v,
+                                  void* grad_pos, int B, int heads, int nq, int nk, int d,
+                                  float inv_scale, void* stream) {
+  SGTA_REQUIRE(q && k && v && grad_out && grad_q && grad_k && grad_v, "sgta_attn_backward: null pointer");
+  SGTA_REQUIRE(B > 0 && B <= 65535 && heads > 0 && nq > 0 && nk > 0, "sgta_attn_backward: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float *Q = (const float*)q, *K = (const float*)k, *V = (const float*)v, *P = (const float*)pos;
+  const float* G = (const float*)grad_out;
+  float *GQ = (float*)grad_q, *GK = (float*)grad_k, *GV = (float*)grad_v, *GP = (float*)grad_pos;
+  switch (d) {
+    case 4: return launch_bwd<4>(Q, K, V, P, G, GQ, GK, GV, GP, B, heads, nq, nk, inv_scale, st);
+    case 8: return launch_bwd<8>(Q, K, V, P, G, GQ, GK, GV, GP, B, heads, nq, nk, inv_scale, st);
+    case 16: return launch_bwd<16>(Q, K, V, P, G, GQ, GK, GV, GP, B, heads, nq, nk, inv_scale, st);
+    case 32: return launch_bwd<32>(Q, K, V, P, G, GQ, GK, GV, GP, B, heads, nq, nk, inv_scale, st);
+    default:
+      set_error("sgta_attn_backward: head dim %d not in {4,8,16,32}", d);
+      return SGTA_EUNSUPPORTED;
+  }
+}

@@ -1,0 +1,412 @@
+// Heatmap decode kernels (memory-bound: one read of the heatmap per launch).
+//
+//   decode_peaks_kernel   -- the LIVE decode of the reference: dream_generic_decode ->
+//       _peaks_info -> peaks_from_belief_maps (sgtapose/lib/model/decode.py:184-313,
+//       lib/model/utils.py:207-284, sgtapose/image_proc.py:1032-1143).  The reference does
+//       this on the CPU with scipy + Python loops (44 ms/frame, >= 7 device syncs); here one
+//       CTA owns one (sample, keypoint) map in shared memory and reproduces scipy's
+//       gaussian_filter(sigma=3) and numpy.average bit for bit (float64, same operation
+//       order, no FMA contraction), so integer peak indices are bit-exact.
+//   nms_topk kernels      -- the alternate decode: _nms + _topk (utils.py:59-103).
+//   soft_argmax_kernel    -- SoftArgmaxPavlo (sgtapose/spatial_softmax.py:24-95).
+#include "common.cuh"
+
+namespace sgta {
+
+struct GaussW { double w[25]; };
+constexpr int GR = 12;                    // int(4.0 * 3 + 0.5)
+constexpr double PEAK_OFFSET = 0.4395;    // utils.py:212
+constexpr float BLUR_THRESH = 0.01f;      // image_proc.py:1043
+constexpr float AMBIG_GAP = 0.25f;        // utils.py:230-233
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  // scipy 'reflect' (half-sample symmetric), any distance outside
+  if (n == 1) return 0;
+  int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - 1 - i;
+}
+
+struct Cand {
+  double cx, cy;
+  float score;
+  int pos;   // row-major pixel position (np.nonzero order); INT_MAX = empty
+};
+
+__device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {
+  // order of sorted(peaks, key=cy, reverse=True) with Python's stable sort
+  if (a.pos == 0x7fffffff) return false;
+  if (b.pos == 0x7fffffff) return true;
+  return a.cy > b.cy || (a.cy == b.cy && a.pos < b.pos);
+}
+__device__ __forceinline__ void cand_insert(const Cand& c, Cand& first, Cand& second) {
+  if (cand_before(c, first)) { second = first; first = c; }
+  else if (cand_before(c, second)) { second = c; }
+}
+
+__device__ __forceinline__ double np_sum25(const double* a) {
+  // numpy pairwise_sum for n = 25 (< 128): 8 interleaved accumulators over the first 24
+  // elements, tree-combined, then the tail
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+#pragma unroll
+  for (int i = 8; i < 24; i += 8)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  return __dadd_rn(res, a[24]);
+}
+
+// grid: B*C CTAs, 256 threads; smem: 3 maps of h*w floats + 256 Cand pairs
+__global__ void __launch_bounds__(256)
+decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
+                    const float* __restrict__ tracking, float* __restrict__ scores,
+                    long long* __restrict__ inds, long long* __restrict__ xs,
+                    long long* __restrict__ ys, float* __restrict__ cts_wreg,
+                    float* __restrict__ trk, GaussW gw, int C, int h, int w) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int hw = h * w;
+  float* ori = reinterpret_cast<float*>(dsm);
+  float* tmp = ori + hw;
+  float* blr = tmp + hw;
+  Cand* cands = reinterpret_cast<Cand*>(dsm + ((sizeof(float) * 3 * hw + 15) / 16) * 16);
+  __shared__ int s_count;
+  const int tid = threadIdx.x;
+  const int bc = blockIdx.x, b = bc / C;
+  const float* src = hm + (long long)bc * hw;
+  if (tid == 0) s_count = 0;
+  for (int e = tid; e < hw; e += 256) ori[e] = __ldg(src + e);
+  __syncthreads();
+
+  // pass 1: correlate along axis 0 (rows), float64 accumulate, float32 store
+  for (int e = tid; e < hw; e += 256) {
+    int y = e / w, x = e % w;
+    double t = __dmul_rn((double)ori[e], gw.w[GR]);
+#pragma unroll 4
+    for (int ii = -GR; ii < 0; ++ii) {
+      double a = (double)ori[reflect_idx(y + ii, h) * w + x];
+      double c = (double)ori[reflect_idx(y - ii, h) * w + x];
+      t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gw.w[ii + GR]));
+    }
+    tmp[e] = (float)t;
+  }
+  __syncthreads();
+  // pass 2: along axis 1 (columns)
+  for (int e = tid; e < hw; e += 256) {
+    int y = e / w, x = e % w;
+    const float* row = tmp + y * w;
+    double t = __dmul_rn((double)row[x], gw.w[GR]);
+#pragma unroll 4
+    for (int ii = -GR; ii < 0; ++ii) {
+      double a = (double)row[reflect_idx(x + ii, w)];
+      double c = (double)row[reflect_idx(x - ii, w)];
+      t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gw.w[ii + GR]));
+    }
+    blr[e] = (float)t;
+  }
+  __syncthreads();
+
+  // peak test on the blurred map (0 outside), centroid on the un-blurred one
+  Cand first, second;
+  first.pos = second.pos = 0x7fffffff;
+  first.cx = first.cy = second.cx = second.cy = 0.0;
+  first.score = second.score = 0.f;
+  int mine = 0;
+  for (int e = tid; e < hw; e += 256) {
+    int y = e / w, x = e % w;
+    float v = blr[e];
+    float up = y > 0 ? blr[e - w] : 0.f, dn = y < h - 1 ? blr[e + w] : 0.f;
+    float lf = x > 0 ? blr[e - 1] : 0.f, rt = x < w - 1 ? blr[e + 1] : 0.f;
+    if (!(v >= up && v >= dn && v >= lf && v >= rt && v > BLUR_THRESH)) continue;
+    ++mine;
+    double wts[25], xv[25], yv[25];
+#pragma unroll
+    for (int j = -2; j <= 2; ++j) {        // x offset -> first array index
+#pragma unroll
+      for (int i = -2; i <= 2; ++i) {      // y offset -> second array index
+        int f = (j + 2) * 5 + (i + 2);
+        bool in = (y + i >= 0) && (y + i < h) && (x + j >= 0) && (x + j < w);
+        double wt = in ? (double)ori[(y + i) * w + (x + j)] : 0.0;
+        wts[f] = wt;
+        xv[f] = in ? __dmul_rn((double)(x + j), wt) : 0.0;
+        yv[f] = in ? __dmul_rn((double)(y + i), wt) : 0.0;
+      }
+    }
+    double scl = np_sum25(wts);
+    Cand c;
+    if (scl == 0.0) {
+      c.cx = __dadd_rn((double)x, PEAK_OFFSET);
+      c.cy = __dadd_rn((double)y, PEAK_OFFSET);
+    } else {
+      c.cx = __dadd_rn(__ddiv_rn(np_sum25(xv), scl), PEAK_OFFSET);
+      c.cy = __dadd_rn(__ddiv_rn(np_sum25(yv), scl), PEAK_OFFSET);
+    }
+    c.score = ori[e];
+    c.pos = e;
+    cand_insert(c, first, second);
+  }
+  if (mine) atomicAdd(&s_count, mine);
+  cands[2 * tid] = first;
+  cands[2 * tid + 1] = second;
+  __syncthreads();
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if (tid < stride) {
+      Cand a = cands[2 * tid], c2 = cands[2 * tid + 1];
+      cand_insert(cands[2 * (tid + stride)], a, c2);
+      cand_insert(cands[2 * (tid + stride) + 1], a, c2);
+      cands[2 * tid] = a; cands[2 * tid + 1] = c2;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int count = s_count;
+    Cand a = cands[0], s2 = cands[1];
+    bool found = false;
+    if (count == 1) found = true;
+    else if (count > 1) found = (a.score - s2.score) >= AMBIG_GAP;   // float32 subtraction
+    float sc = -1.f;
+    long long xi = 0, yi = 0;
+    if (found) {
+      xi = (long long)a.cx;   // int(): truncation toward zero
+      yi = (long long)a.cy;
+      // non-negative (post-sigmoid) maps keep the centroid inside the map; clamp only guards
+      // shared memory against negative-weight inputs the reference would fault on
+      xi = xi < 0 ? 0 : (xi > w - 1 ? w - 1 : xi);
+      yi = yi < 0 ? 0 : (yi > h - 1 ? h - 1 : yi);
+      sc = ori[yi * w + xi];
+    }
+    long long ind = yi * w + xi;
+    scores[bc] = sc; inds[bc] = ind; xs[bc] = xi; ys[bc] = yi;
+    float fx = (float)xi, fy = (float)yi;
+    if (reg) {
+      const float* rb = reg + (long long)b * 2 * hw;
+      fx += __ldg(rb + ind); fy += __ldg(rb + hw + ind);
+    } else { fx += 0.5f; fy += 0.5f; }
+    cts_wreg[2 * bc] = fx; cts_wreg[2 * bc + 1] = fy;
+    if (tracking && trk) {
+      const float* tb = tracking + (long long)b * 2 * hw;
+      trk[2 * bc] = __ldg(tb + ind); trk[2 * bc + 1] = __ldg(tb + hw + ind);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// _nms (+ optional per-channel top-K).  grid B*C, 256 threads, smem 2*h*w floats.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_argmax_excluding(const float* vals, int n, const int* taken,
+                                                       int ntaken, float* s_val, int* s_idx,
+                                                       float& outv, int& outi) {
+  float best = -INFINITY; int bi = 0x7fffffff;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    bool tk = false;
+    for (int t = 0; t < ntaken; ++t) tk |= (taken[t] == e);
+    if (tk) continue;
+    float v = vals[e];
+    if (bi == 0x7fffffff || v > best) { best = v; bi = e; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bv = s_val[0]; int bb = s_idx[0];
+    for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) {
+      float ov = s_val[wv]; int oi = s_idx[wv];
+      if (oi != 0x7fffffff && (bb == 0x7fffffff || ov > bv || (ov == bv && oi < bb))) { bv = ov; bb = oi; }
+    }
+    s_val[0] = bv; s_idx[0] = bb;
+  }
+  __syncthreads();
+  outv = s_val[0]; outi = s_idx[0];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+nms_topk_channel_kernel(const float* __restrict__ hm, float* __restrict__ nms_out,
+                        float* __restrict__ ws_val, int* __restrict__ ws_idx, int h, int w, int K) {
+  extern __shared__ __align__(16) float nsm[];
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_taken[64];
+  const int hw = h * w;
+  float* ori = nsm;
+  float* kept = nsm + hw;
+  const float* src = hm + (long long)blockIdx.x * hw;
+  for (int e = threadIdx.x; e < hw; e += 256) ori[e] = __ldg(src + e);
+  __syncthreads();
+  for (int e = threadIdx.x; e < hw; e += 256) {
+    int y = e / w, x = e % w;
+    float v = ori[e], mx = v;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        int yy = y + dy, xx = x + dx;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) mx = fmaxf(mx, ori[yy * w + xx]);
+      }
+    float kv = v * ((mx == v) ? 1.f : 0.f);
+    kept[e] = kv;
+    if (nms_out) nms_out[(long long)blockIdx.x * hw + e] = kv;
+  }
+  __syncthreads();
+  for (int r = 0; r < K; ++r) {
+    float bv; int bi;
+    block_argmax_excluding(kept, hw, s_taken, r, s_val, s_idx, bv, bi);
+    if (threadIdx.x == 0) {
+      s_taken[r] = bi;
+      ws_val[(long long)blockIdx.x * K + r] = bv;
+      ws_idx[(long long)blockIdx.x * K + r] = bi;
+    }
+    __syncthreads();
+  }
+}
+
+// grid B, 256 threads: top-K over the C*K per-channel candidates (value desc, position asc)
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ ws_val, const int* __restrict__ ws_idx,
+                  float* __restrict__ scores, long long* __restrict__ inds, int* __restrict__ clses,
+                  int CK, int K) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_taken[64];
+  const float* vals = ws_val + (long long)blockIdx.x * CK;
+  for (int r = 0; r < K; ++r) {
+    float bv; int bi;
+    block_argmax_excluding(vals, CK, s_taken, r, s_val, s_idx, bv, bi);
+    if (threadIdx.x == 0) {
+      s_taken[r] = bi;
+      scores[(long long)blockIdx.x * K + r] = bv;
+      inds[(long long)blockIdx.x * K + r] = ws_idx[(long long)blockIdx.x * CK + bi];
+      clses[(long long)blockIdx.x * K + r] = bi / K;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// SoftArgmaxPavlo: 7x7 average pool (zeros counted), softmax(beta * (pooled - max)), E[x], E[y]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+soft_argmax_kernel(const float* __restrict__ hm, float* __restrict__ out, int h, int w, float beta,
+                   float size_mult) {
+  extern __shared__ __align__(16) float ssm[];
+  __shared__ float s_red[3][8];
+  const int hw = h * w;
+  float* ori = ssm;
+  float* pooled = ssm + hw;
+  const float* src = hm + (long long)blockIdx.x * hw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < hw; e += 256) ori[e] = __ldg(src + e);
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int e = threadIdx.x; e < hw; e += 256) {
+    int y = e / w, x = e % w;
+    float s = 0.f;
+    for (int dy = -3; dy <= 3; ++dy) {
+      int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -3; dx <= 3; ++dx) {
+        int xx = x + dx;
+        if (xx >= 0 && xx < w) s += ori[yy * w + xx];
+      }
+    }
+    s = s / 49.f;
+    pooled[e] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[0][warp] = mx;
+  __syncthreads();
+  mx = s_red[0][0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[0][i]);
+  __syncthreads();
+  float se = 0.f, sx = 0.f, sy = 0.f;
+  for (int e = threadIdx.x; e < hw; e += 256) {
+    int y = e / w, x = e % w;
+    float ex = expf(beta * (pooled[e] - mx));
+    se += ex; sx += ex * ((float)x * size_mult); sy += ex * ((float)y * size_mult);
+  }
+  se = warp_sum(se); sx = warp_sum(sx); sy = warp_sum(sy);
+  if (lane == 0) { s_red[0][warp] = se; s_red[1][warp] = sx; s_red[2][warp] = sy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bx = 0.f, by = 0.f;
+    for (int i = 0; i < 8; ++i) { a += s_red[0][i]; bx += s_red[1][i]; by += s_red[2][i]; }
+    float inv = 1.f / (a + 1e-8f);
+    out[2 * blockIdx.x] = bx * inv;
+    out[2 * blockIdx.x + 1] = by * inv;
+  }
+}
+
+}  // namespace sgta
+
+using namespace sgta;
+
+extern "C" int sgta_decode_peaks(const void* hm, const void* reg, const void* tracking, void* scores,
+                                 void* inds, void* xs, void* ys, void* cts_wreg, void* trk,
+                                 const double* gauss_w, int B, int C, int h, int w, void* stream) {
+  SGTA_REQUIRE(hm && scores && inds && xs && ys && cts_wreg && gauss_w, "sgta_decode_peaks: null pointer");
+  SGTA_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0, "sgta_decode_peaks: bad shape");
+  SGTA_REQUIRE(!tracking || trk, "sgta_decode_peaks: tracking given without an output buffer");
+  size_t maps = ((sizeof(float) * 3 * (size_t)h * w + 15) / 16) * 16;
+  size_t smem = maps + sizeof(Cand) * 512;
+  SGTA_REQUIRE(smem <= 220 * 1024, "sgta_decode_peaks: heatmap %dx%d too large for shared memory", h, w);
+  GaussW gw;
+  for (int i = 0; i < 25; ++i) gw.w[i] = gauss_w[i];
+  cudaFuncSetAttribute(decode_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  decode_peaks_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>(
+      (const float*)hm, (const float*)reg, (const float*)tracking, (float*)scores, (long long*)inds,
+      (long long*)xs, (long long*)ys, (float*)cts_wreg, (float*)trk, gw, C, h, w);
+  return check_launch("decode_peaks_kernel");
+}
+
+static int launch_nms(const void* hm, void* nms_out, float* ws_val, int* ws_idx, int B, int C, int h,
+                      int w, int K, cudaStream_t st) {
+  size_t smem = sizeof(float) * 2 * (size_t)h * w;
+  SGTA_REQUIRE(smem <= 220 * 1024, "nms: heatmap %dx%d too large for shared memory", h, w);
+  cudaFuncSetAttribute(nms_topk_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  nms_topk_channel_kernel<<<B * C, 256, smem, st>>>((const float*)hm, (float*)nms_out, ws_val, ws_idx,
+                                                   h, w, K);
+  return check_launch("nms_topk_channel_kernel");
+}
+
+extern "C" int sgta_decode_nms_topk(const void* hm, void* scores, void* inds, void* clses,
+                                    void* workspace, int B, int C, int h, int w, int K, void* stream) {
+  SGTA_REQUIRE(hm && scores && inds && clses && workspace, "sgta_decode_nms_topk: null pointer");
+  SGTA_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0 && K > 0 && K <= 64 && K <= h * w,
+               "sgta_decode_nms_topk: bad shape (K <= 64)");
+  float* ws_val = (float*)workspace;
+  int* ws_idx = (int*)(ws_val + (size_t)B * C * K);
+  int rc = launch_nms(hm, nullptr, ws_val, ws_idx, B, C, h, w, K, (cudaStream_t)stream);
+  if (rc) return rc;
+  topk_merge_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(ws_val, ws_idx, (float*)scores,
+                                                        (long long*)inds, (int*)clses, C * K, K);
+  return check_launch("topk_merge_kernel");
+}
+
+extern "C" int sgta_nms3x3(const void* hm, void* out, int B, int C, int h, int w, void* stream) {
+  SGTA_REQUIRE(hm && out, "sgta_nms3x3: null pointer");
+  SGTA_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0, "sgta_nms3x3: bad shape");
+  return launch_nms(hm, out, nullptr, nullptr, B, C, h, w, 0, (cudaStream_t)stream);
+}
+
+extern "C" int sgta_soft_argmax(const void* hm, void* out, int B, int C, int h, int w, float beta,
+                                float size_mult, void* stream) {
+  SGTA_REQUIRE(hm && out, "sgta_soft_argmax: null pointer");
+  SGTA_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0, "sgta_soft_argmax: bad shape");
+  size_t smem = sizeof(float) * 2 * (size_t)h * w;
+  SGTA_REQUIRE(smem <= 220 * 1024, "sgta_soft_argmax: heatmap too large for shared memory");
+  cudaFuncSetAttribute(soft_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  soft_argmax_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>((const float*)hm, (float*)out, h, w,
+                                                                beta, size_mult);
+  return check_launch("soft_argmax_kernel");
+}

@@ -1,0 +1,172 @@
+"""Structure-prior temporal attention: host side of the token path and attention core.
+
+Mirrors, with the same names and argument meaning, the reference functions in
+sgtapose/lib/model/networks/dla.py: get_topk_index (:898-913), get_topk_features_scale
+(:915-968), substitute_topk_features_scale (:1006-1018) and MHCA_ein (:848-887), but every
+step runs in a CUDA kernel of libsgta_b200.so; no index tensor ever visits the host.
+
+Defined behaviour where the reference is tie-/order-dependent:
+top-k ties -> lowest index first; duplicate write-back indices -> highest token index wins.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+def topk_flat_index(hm, K):
+    """[B,C,H,W] fp32 -> [B, C*K] int64 flat indices (value desc, index asc)."""
+    B, C, H, W = hm.shape
+    hm = hm.contiguous().float()
+    idx = torch.empty(B, C * K, device=hm.device, dtype=torch.int64)
+    _lib.call("sgta_topk_index", _lib.ptr(hm), _lib.ptr(idx), B, C, H * W, K, _lib.stream())
+    return idx
+
+
+def get_topk_index(pre_hm, repro_hm, K):
+    """dla.py:898-913.  Returns ([B,C*K,2], [B,C*K,2]) fp32 (x, y) like the reference, but as
+    CUDA tensors (the reference returns CPU tensors and pays a sync per level)."""
+    assert pre_hm.shape == repro_hm.shape
+    W = pre_hm.shape[3]
+    out = []
+    for hm in (pre_hm, repro_hm):
+        idx = topk_flat_index(hm, K)
+        out.append(torch.stack([(idx % W).float(), torch.div(idx, W, rounding_mode="floor").float()], -1))
+    return out[0], out[1]
+
+
+def window_ids(flat_idx, Whm, scale, kernel, H, W):
+    """[B,CK] int64 flat prior indices -> [B, CK*win^2] int64 feature-map ids with the
+    reference's fp32 index arithmetic (dla.py:932-957)."""
+    B, CK = flat_idx.shape
+    win = 2 * (kernel // 2) + 1
+    ids = torch.empty(B, CK * win * win, device=flat_idx.device, dtype=torch.int64)
+    _lib.call("sgta_window_ids", _lib.ptr(flat_idx), _lib.ptr(ids), B, CK, Whm, float(scale),
+              kernel, H, W, _lib.stream())
+    return ids
+
+
+def gather_tokens(feats, ids):
+    """rows[b,t,:] = feats[b,:,ids[b,t]]; feats NCHW fp32.  Differentiable w.r.t. feats."""
+    if torch.is_grad_enabled() and feats.requires_grad:
+        B, C, H, W = feats.shape
+        flat = feats.reshape(B, C, H * W).permute(0, 2, 1)
+        return torch.gather(flat, 1, ids[..., None].expand(-1, -1, C))
+    B, C, H, W = feats.shape
+    feats = feats.contiguous().float()
+    n = ids.shape[1]
+    rows = torch.empty(B, n, C, device=feats.device, dtype=torch.float32)
+    _lib.call("sgta_gather_tokens", _lib.ptr(feats), _lib.ptr(ids), _lib.ptr(rows), B, C, H * W, n, 0,
+              _lib.stream())
+    return rows
+
+
+def _last_writer_mask(ids):
+    """mask[b,t] = no later token carries the same id (training-time twin of the kernel rule)."""
+    B, n = ids.shape
+    order = torch.arange(n, device=ids.device)
+    key = ids * n + order[None]
+    srt, perm = torch.sort(key, dim=1)
+    sid = torch.div(srt, n, rounding_mode="floor")
+    last = torch.ones_like(sid, dtype=torch.bool)
+    last[:, :-1] = sid[:, :-1] != sid[:, 1:]
+    mask = torch.zeros_like(last)
+    mask.scatter_(1, perm, last)
+    return mask
+
+
+def scatter_tokens(feats, ids, rows):
+    """Returns a copy of feats with feats[b,:,ids[b,t]] = rows[b,t,:]; highest t wins."""
+    B, C, H, W = feats.shape
+    if torch.is_grad_enabled() and (feats.requires_grad or rows.requires_grad):
+        mask = _last_writer_mask(ids)
+        flat = feats.reshape(B, C, H * W).permute(0, 2, 1)
+        bidx = torch.arange(B, device=ids.device)[:, None].expand_as(ids)
+        out = flat.index_put((bidx[mask], ids[mask]), rows[mask])
+        return out.permute(0, 2, 1).reshape(B, C, H, W).contiguous()
+    out = feats.contiguous().float().clone()
+    rows = rows.contiguous().float()
+    n = ids.shape[1]
+    _lib.call("sgta_scatter_tokens", _lib.ptr(out), _lib.ptr(ids), _lib.ptr(rows), B, C, H * W, n, 0,
+              _lib.stream())
+    return out
+
+
+def get_topk_features_scale(feats, topk_inds, scale_num, kernel=3):
+    """dla.py:915-968.  topk_inds: [B,K,2] fp32 (x,y) as returned by get_topk_index.
+    Returns (selected_feat [B,K*N,C], batch_id [B,K*N], feat_id [B,K*N])."""
+    B, C, H, W = feats.shape
+    assert H == W
+    flat = (topk_inds[..., 1].long() * 65536 + topk_inds[..., 0].long()).contiguous()
+    ids = window_ids(flat, 65536, scale_num, kernel, H, W)
+    batch_id = torch.arange(B, device=feats.device)[:, None].expand_as(ids)
+    return gather_tokens(feats, ids), batch_id, ids
+
+
+def substitute_topk_features_scale(out, cur_features, batch_id, feat_id, mlp):
+    """dla.py:1006-1018."""
+    cur_query = gather_tokens(cur_features, feat_id)
+    rows = mlp(torch.cat([out, cur_query], dim=-1))
+    return scatter_tokens(cur_features, feat_id, rows)
+
+
+class _AttnCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, pos, heads, inv_scale):
+        if not q.is_cuda:
+            raise _lib.SgtaError("attention: inputs must be CUDA tensors (no CPU fallback)")
+        q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+        pos_c = pos.contiguous().float() if pos is not None else None
+        B, nq, HD = q.shape
+        nk = k.shape[1]
+        d = HD // heads
+        out = torch.empty_like(q)
+        _lib.call("sgta_attn_forward", _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(pos_c),
+                  _lib.ptr(out), B, heads, nq, nk, d, float(inv_scale), _lib.stream())
+        ctx.save_for_backward(q, k, v, pos_c if pos_c is not None else q.new_empty(0))
+        ctx.cfg = (heads, inv_scale, pos is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, v, pos = ctx.saved_tensors
+        heads, inv_scale, has_pos = ctx.cfg
+        go = go.contiguous().float()
+        B, nq, HD = q.shape
+        nk = k.shape[1]
+        gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        gpos = torch.zeros_like(pos) if (has_pos and ctx.needs_input_grad[3]) else None
+        _lib.call("sgta_attn_backward", _lib.ptr(q), _lib.ptr(k), _lib.ptr(v),
+                  _lib.ptr(pos) if has_pos else None, _lib.ptr(go), _lib.ptr(gq), _lib.ptr(gk),
+                  _lib.ptr(gv), _lib.ptr(gpos), B, heads, nq, nk, HD // heads, float(inv_scale),
+                  _lib.stream())
+        return gq, gk, gv, gpos, None, None
+
+
+def attention_core(q, k, v, pos, heads, scale):
+    """softmax(q k^T / scale + pos) v on "b n (h d)" tensors, fused on the device."""
+    return _AttnCore.apply(q, k, v, pos, heads, 1.0 / scale)
+
+
+class MHCA_ein(nn.Module):
+    """dla.py:848-887, same parameters (w_q, w_k, w_v, fc, pos_embed)."""
+
+    def __init__(self, num_heads, inp_dim, hid_dim, n, pos_embed=True):
+        super().__init__()
+        assert hid_dim % num_heads == 0
+        self.hid_dim, self.inp_dim, self.n_heads, self.n = hid_dim, inp_dim, num_heads, n
+        self.pos_embed_bool = pos_embed
+        self.w_q = nn.Linear(inp_dim, hid_dim, bias=False)
+        self.w_k = nn.Linear(inp_dim, hid_dim, bias=False)
+        self.w_v = nn.Linear(inp_dim, hid_dim, bias=False)
+        self.fc = nn.Linear(hid_dim, inp_dim)
+        self.scale = math.sqrt(hid_dim // num_heads)
+        self.pos_embed = nn.Parameter(torch.zeros(num_heads, n, n))
+
+    def forward(self, query, key, value):
+        pos = self.pos_embed if (self.pos_embed is not None and self.pos_embed_bool) else None
+        out = attention_core(self.w_q(query), self.w_k(key), self.w_v(value), pos, self.n_heads,
+                             self.scale)
+        return self.fc(out)
