@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- pose frames/s of the SGTAPose per-frame dense inference path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one pass of the hot path over one lock-step batch of B clips (one frame-pair
+each, 384x384, 7 Panda keypoints): network forward (DLA-34 x2 + structure-prior attention +
+DLAUp/IDAUp with 16 DCNs + heads) -> sigmoid -> live heatmap decode.  Workload =
+BASELINE.json configs[1] ("same model fp32 batch 32 on 1xB200"); N>1 shards clips across
+ranks (weak scaling, B clips per GPU) and all-gathers the decoded keypoints over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed frames/s with inputs resident in
+HBM; `e2e` = the same through the public API with HOST (pinned) inputs, H2D and D2H inside
+the timed region; `roofline` = the DCN kernels (tensor bound) timed live with CUDA events;
+`cpu_baseline` = the oracle port (torch CPU + torchvision deform_conv2d + numpy decode) on
+the host cores, bounded sample.  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S = 384
+DCN_GFLOP_PER_FRAME = 7.984          # sum 2*Cout*9Cin*H*W over the 16 DCNs
+TOTAL_GFLOP_PER_FRAME = 56.6
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(device):
+    from sgtapose_b200 import config, networks, synth
+    opt = config.default_opt()
+    model = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), opt)
+    sd = synth.synthetic_state_dict(model.state_dict(), seed=317)
+    model.load_state_dict(sd)
+    return model.eval().to(device), sd, opt
+
+
+def cpu_reference_fps(sd, steps, warmup, B=1):
+    """The reference's CPU path restated (oracle/): fp32 torch + torchvision deform_conv2d +
+    numpy live decode, all host threads."""
+    from oracle import decode as odec
+    from oracle import model as omodel
+    from sgtapose_b200 import synth
+    torch.set_num_threads(os.cpu_count())
+    ins = synth.synthetic_inputs(B, S, seed=317, frame=1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = omodel.forward(sd, *ins)[0]
+        hm = torch.sigmoid(out["hm"]).numpy()
+        odec.dream_generic_decode(hm, out["reg"].numpy(), out["tracking"].numpy())
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return B / med, med, os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sgtapose_b200 import config, networks, synth
+    model = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
+    sd = synth.synthetic_state_dict(model.state_dict(), seed=317)
+    fps, med, cores = cpu_reference_fps(sd, args.steps, args.warmup)
+    sample = "batch 1 frame-pair 384x384 per step (the GPU arm runs %d per step), median of %d steps" % (
+        args.batch, args.steps)
+    line = {"impl": "reference", "metric": "pose_frames_per_sec", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: DLA-34+DCN SGTAPose forward + live decode, 384x384, "
+                                   "2-frame synthetic Panda, fp32", "batch_per_step": 1},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from sgtapose_b200 import _lib, decode, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    B = args.batch
+    model, sd, opt = build_model(dev)
+    model.skip_dead_levels = bool(args.skip_dead_levels)
+    host = [t.pin_memory() for t in synth.synthetic_inputs(B, S, seed=317 + rank, frame=1)]
+    resident = [t.to(dev, non_blocking=True) for t in host]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def step(inputs):
+        with torch.no_grad():
+            out = model(*inputs)[0]
+            out["hm"] = out["hm"].sigmoid_()                    # sgta_detector.py:854-862
+            return decode.dream_generic_decode(out, K=7, opt=opt)
+
+    def step_e2e():
+        dets = step([t.to(dev, non_blocking=True) for t in host])
+        res = {k: dets[k].cpu() for k in ("scores", "cts_wreg", "xs", "ys", "tracking")}
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step(resident)
+    barrier()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        dets = step(resident)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end: host inputs, H2D + D2H inside the timed region
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    d2h = sum(v.numel() * v.element_size() for v in res.values())
+
+    # per-kernel timing of the DCN launches (CUDA events on the launching stream)
+    dcn_ms = time_dcn_kernels(lambda: step(resident))
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.empty_like(dets["cts_wreg"]) for _ in range(world)]
+        dist.all_gather(gathered, dets["cts_wreg"].contiguous())        # per-rank poses -> everyone
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, which = _peaks()
+    frames = B * world * args.steps
+    value = frames / (ms / 1e3)
+    dcn_tflops = DCN_GFLOP_PER_FRAME * B / (dcn_ms / 1e3) / 1e3
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    line = {
+        "metric": "pose_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: DLA-34+DCN SGTAPose forward + live decode, 384x384, 2-frame "
+                               "synthetic Panda, fp32", "batch_per_gpu": B, "clips_sharded_by": "rank",
+                   "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2",
+                   "skip_dead_levels": bool(args.skip_dead_levels), "engine": "eager+libsgta_b200"},
+        "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "dcn (16 launches/step)", "achieved": dcn_tflops,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": dcn_tflops / peak_tf, "traffic": None,
+                     "peak_source": which + " bf16 sustained", "ms_per_step": dcn_ms},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        fps, med, cores = cpu_reference_fps(sd, 5, 2)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "5 timed frame-pairs (batch 1) after 2 warm-ups, median"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_dcn_kernels(fn):
+    """Sum of the DCN kernel durations of one step, each launch bracketed by CUDA events."""
+    from sgtapose_b200 import _lib
+    events = []
+    orig = _lib.call
+
+    def timed(name, *a):
+        if name.startswith("sgta_dcn_forward"):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig(name, *a)
+            e.record()
+            events.append((s, e))
+        else:
+            orig(name, *a)
+
+    _lib.call = timed
+    try:
+        tot = []
+        for _ in range(3):
+            events.clear()
+            fn()
+            torch.cuda.synchronize()
+            tot.append(sum(s.elapsed_time(e) for s, e in events))
+    finally:
+        _lib.call = orig
+    return sorted(tot)[1]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--skip-dead-levels", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

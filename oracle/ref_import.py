@@ -124,21 +124,7 @@ def load_reference(dcn_cls=None):
     return ns
 
 
-def default_opt(**over):
-    """The `opt` fields the model reads."""
-    o = types.SimpleNamespace(
-        pre_img=True, pre_hm=True, ct_modify=False, head_kernel=3, prior_bias=-4.6,
-        dla_node="dcn", load_model="x", model_output_list=False, num_classes=7,
-        pos_embed=True, zero_tracking=False,
-        k_list_1=1, k_list_2=1, k_list_3=1, k_list_4=1, k_list_5=1, k_list_6=1,
-        ks1=12, ks2=6, ks3=3, ks4=1, ks5=1, ks6=1)
-    for k, v in over.items():
-        setattr(o, k, v)
-    return o
-
-
-HEADS = {"hm": 7, "reg": 2, "wh": 2, "tracking": 2}
-HEAD_CONV = {h: [256] for h in HEADS}
+from sgtapose_b200.config import HEAD_CONV, HEADS, default_opt  # noqa: E402,F401  (shared description)
 
 
 def build_reference_model(ns=None, opt=None):
