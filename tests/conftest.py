@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    import torch
+    # fp32 parity: the eager module tree runs its plain convolutions / linears through
+    # cuDNN / cuBLAS, which default to TF32 (1e-3 relative per op) unless told otherwise
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
 

@@ -185,7 +185,7 @@ def test_topk_k3_and_gather_scatter_vs_oracle():
     ref_sc = omodel.scatter_tokens(feats, ids, new_rows)
     got_sc = fusion.scatter_tokens(feats.to(DEV), ids.to(DEV), new_rows.to(DEV)).cpu()
     assert torch.equal(got_sc, ref_sc)
-    assert (ids[0, :9] == ids[0, 9:18]).all()     # duplicates present: all-zero map -> same window
+    assert len(set(ids[0, :9].tolist())) < 9            # clamped corner window -> duplicate ids exercised
 
 
 # ------------------------------------------------------------------------------------ decode
