@@ -295,3 +295,130 @@ def test_dcn_umma_vs_oracle(cfg, mode):
     err = rel_err(got, ref)
     # fp32 parity mode: north_star bound 1e-3 relative (we hold 1e-4); bf16 mode: stated looser bound 2e-2
     assert err < (1e-4 if mode == "f32x3" else 2e-2), err
+
+
+# ------------------------------------------------------------------------------------ plain convs on tcgen05
+CONV_CFGS = [  # B, Cin, Cout, H, W, k, stride, pad
+    (2, 64, 64, 24, 24, 3, 1, 1),
+    (1, 16, 16, 40, 40, 3, 1, 1),
+    (1, 16, 32, 40, 40, 3, 2, 1),
+    (1, 32, 64, 30, 30, 3, 2, 1),
+    (2, 128, 256, 12, 12, 3, 1, 1),
+    (1, 256, 512, 12, 12, 3, 2, 1),
+    (1, 448, 128, 12, 12, 1, 1, 0),
+    (1, 32, 64, 24, 24, 1, 1, 0),
+    (1, 64, 768, 16, 16, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("cfg", CONV_CFGS)
+@pytest.mark.parametrize("mode", ["f32x3", "bf16"])
+def test_conv_umma_vs_torch(cfg, mode):
+    import torch.nn.functional as F
+    from sgtapose_b200 import fastops as fo
+    B, Ci, Co, H, W, k, st, pad = cfg
+    x = C.gen(31, B, Ci, H, W)
+    w = C.gen(32, Co, Ci, k, k) * (1.0 / (Ci * k * k)) ** 0.5
+    scale = C.gen(33, Co).abs() + 0.5
+    shift = C.gen(34, Co) * 0.2
+    Ho, Wo = (H + 2 * pad - k) // st + 1, (W + 2 * pad - k) // st + 1
+    res = C.gen(35, B, Co, Ho, Wo)
+    ref = torch.relu(F.conv2d(x, w, None, st, pad) * scale[None, :, None, None] + shift[None, :, None, None] + res)
+    m = fo.MMA_F32X3 if mode == "f32x3" else fo.MMA_BF16
+    adt = torch.float32 if mode == "f32x3" else torch.bfloat16
+    spec = fo.ConvSpec(fo.weight_matrix(w.to(DEV)), scale.to(DEV), shift.to(DEV), Ci, k, k, st, pad, m, fo.ACT_RELU)
+    # input lives in a wider buffer (channel slice), output too: exercises ldx / ldy / offsets
+    xbuf = torch.zeros(B, H, W, Ci + 64, device=DEV, dtype=adt)
+    xbuf[..., 64:] = x.to(DEV).permute(0, 2, 3, 1).to(adt)
+    rbuf = res.to(DEV).permute(0, 2, 3, 1).contiguous().to(adt)
+    ybuf = torch.zeros(B, Ho, Wo, Co + 16, device=DEV, dtype=torch.float32)
+    fo.conv_nhwc(spec, xbuf, B, H, W, Ci + 64, ybuf, Co + 16, x_coff=64, y_coff=16, res=rbuf, ldres=Co)
+    got = ybuf[..., 16:].permute(0, 3, 1, 2).cpu()
+    assert float(ybuf[..., :16].abs().max()) == 0.0
+    err = rel_err(got, ref)
+    assert err < (1e-4 if mode == "f32x3" else 2e-2), err
+
+
+def test_conv_stem_and_nchw_epilogue():
+    import torch.nn.functional as F
+    from sgtapose_b200 import fastops as fo
+    B, S = 2, 40
+    img, hm = C.gen(41, B, 3, S, S), C.gen(42, B, 1, S, S).abs()
+    wi, wh = C.gen(43, 16, 3, 7, 7) * 0.1, C.gen(44, 16, 1, 7, 7) * 0.2
+    sc, sh = C.gen(45, 32).abs() + 0.5, C.gen(46, 32) * 0.3
+    ref = torch.relu(F.conv2d(img, wi, None, 1, 3) * sc[None, :16, None, None] + sh[None, :16, None, None]) + \
+        torch.relu(F.conv2d(hm, wh, None, 1, 3) * sc[None, 16:, None, None] + sh[None, 16:, None, None])
+    wm = torch.cat([fo.weight_matrix(wi, 4, 0), fo.weight_matrix(wh, 4, 3)], 0).to(DEV)
+    spec = fo.ConvSpec(wm, sc.to(DEV), sh.to(DEV), 4, 7, 7, 1, 3, fo.MMA_F32X3)
+    in4 = torch.zeros(B, S, S, 4, device=DEV)
+    fo.nchw_to_nhwc(img.to(DEV), in4, 4, 0)
+    fo.nchw_to_nhwc(hm.to(DEV), in4, 4, 3)
+    assert torch.equal(in4[..., :3].permute(0, 3, 1, 2).cpu(), img) and torch.equal(in4[..., 3].cpu(), hm[:, 0])
+    y = torch.zeros(B, S, S, 16, device=DEV)
+    fo.conv_nhwc(spec, in4, B, S, S, 4, y, 16, epi=fo.EPI_STEM)
+    assert rel_err(y.permute(0, 3, 1, 2).cpu(), ref) < 1e-4
+    # 1x1 conv 256 -> 7 with NCHW fp32 output and fused sigmoid, reading a channel slice
+    hid = C.gen(47, B, 512, 12, 12)
+    w2, b2 = C.gen(48, 7, 256, 1, 1) * 0.1, C.gen(49, 7)
+    ref2 = torch.sigmoid(F.conv2d(hid[:, 256:], w2, b2))
+    spec2 = fo.ConvSpec(fo.weight_matrix(w2.to(DEV)), torch.ones(7, device=DEV), b2.to(DEV), 256, 1, 1, 1, 0,
+                        fo.MMA_F32X3, fo.ACT_SIGMOID, n_valid=7)
+    hb = hid.to(DEV).permute(0, 2, 3, 1).contiguous()
+    out = torch.zeros(B, 7, 12, 12, device=DEV)
+    fo.conv_nhwc(spec2, hb, B, 12, 12, 512, out, 0, x_coff=256, epi=fo.EPI_NCHW)
+    assert rel_err(out.cpu(), ref2) < 1e-4
+    back = torch.zeros(B, 512, 12, 12, device=DEV)
+    fo.nhwc_to_nchw(hb, back, 512, 512)
+    assert torch.equal(back.cpu(), hid)
+
+
+def test_maxpool_and_upsample_add():
+    import torch.nn.functional as F
+    from sgtapose_b200 import fastops as fo
+    B, Cc, H = 2, 64, 12
+    x = C.gen(51, B, Cc, H, H)
+    xb = x.to(DEV).permute(0, 2, 3, 1).contiguous()
+    y = torch.zeros(B, H // 2, H // 2, Cc + 32, device=DEV)
+    fo.maxpool2(xb, B, H, H, Cc, Cc, y, Cc + 32, y_coff=32)
+    assert torch.equal(y[..., 32:].permute(0, 3, 1, 2).cpu(), F.max_pool2d(x, 2, 2))
+    for f in (2, 4):
+        w = C.gen(52 + f, Cc, 1, 2 * f, 2 * f).abs()
+        skip = C.gen(60 + f, B, Cc, H * f, H * f)
+        ref = F.conv_transpose2d(x, w, None, stride=f, padding=f // 2, groups=Cc) + skip
+        sb = skip.to(DEV).permute(0, 2, 3, 1).contiguous()
+        out = torch.zeros(B, H * f, H * f, Cc, device=DEV)
+        fo.upsample_add(xb, w.to(DEV), sb, Cc, out, Cc, B, H, H, Cc, f)
+        assert rel_err(out.permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ whole engine
+@pytest.mark.parametrize("mode,graph", [("fp32", False), ("fp32", True), ("bf16", True)])
+def test_engine_golden(golden, mode, graph):
+    """The compiled NHWC engine vs the REFERENCE's outputs on the same inputs and weights."""
+    from sgtapose_b200 import config, engine, networks, synth
+    g = golden("model_S128.npz")
+    m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=C.GOLDEN_SEED)
+    eng = engine.InferenceEngine(sd, config.default_opt(), batch=2, size=128, mode=mode, device=DEV,
+                                 use_graph=graph)
+    ins = synth.synthetic_inputs(2, 128, seed=C.GOLDEN_SEED, frame=1)
+    for rep in range(2):                       # second call exercises graph replay
+        out = eng(*[t.to(DEV) for t in ins])[0]
+    tol = 1e-3 if mode == "fp32" else 6e-2
+    feat = eng.feat.float().permute(0, 3, 1, 2).cpu()
+    assert rel_err(feat, torch.from_numpy(g["feat"])) < tol
+    for k in ("hm", "reg", "tracking"):
+        assert rel_err(out[k].cpu(), torch.from_numpy(g[k])) < tol, k
+
+
+def test_engine_infer_matches_oracle_decode():
+    from sgtapose_b200 import config, engine, networks, synth
+    m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=3)
+    eng = engine.InferenceEngine(sd, config.default_opt(), batch=2, size=128, mode="fp32", device=DEV)
+    ins = [t.to(DEV) for t in synth.synthetic_inputs(2, 128, seed=3, frame=1)]
+    det = eng.infer(*ins)
+    out = eng(*ins)[0]
+    ref = odec.dream_generic_decode(torch.sigmoid(out["hm"]).cpu().numpy(), out["reg"].cpu().numpy(),
+                                    out["tracking"].cpu().numpy())
+    assert np.array_equal(det["xs"].cpu().numpy(), ref["xs"]) and np.array_equal(det["ys"].cpu().numpy(), ref["ys"])
