@@ -76,9 +76,8 @@ int sgta_dcn_backward(const void* x, const void* offset_mask, const void* weight
 #define SGTA_ACT_NONE 0
 #define SGTA_ACT_RELU 1
 #define SGTA_ACT_SIGMOID 2
-#define SGTA_EPI_NHWC 0   /* y[p*ldy + o]                                              */
-#define SGTA_EPI_STEM 1   /* Cout==32: y[p*ldy + c] = relu(a[c]) + relu(a[16+c]), c<16  */
-#define SGTA_EPI_NCHW 2   /* fp32 y[(b*n_valid + o)*Ho*Wo + pix], o < n_valid           */
+/* epi (NHWC path): 0 = y[p*ldy + o]; 1 = stem, Cout==32: y[p*ldy + c] = relu(a[c]) +
+ * relu(a[16+c]), c<16; 2 = fp32 NCHW y[(b*n_valid + o)*Ho*Wo + pix], o < n_valid */
 
 /* DCNv2 (3x3, stride 1, pad 1, dil 1, dg 1: the configuration dla.py:545 constructs),
  * Cin % 64 == 0, Cout % 16 == 0, 16 <= Cout <= 256.
@@ -130,6 +129,89 @@ int sgta_gather_tokens_nhwc(const void* feats, int64_t ld, const void* ids, void
                             int C, int HW, int n, int dtype, void* stream);
 int sgta_scatter_tokens_nhwc(void* feats, int64_t ld, const void* ids, const void* rows, int B,
                              int C, int HW, int n, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * B200 engine path: zero-bordered "planes" activation layouts + tcgen05 shift-GEMM /
+ * gather-GEMM convolutions (csrc/planes.cuh, conv_planes.cu, planes_ops.cu).
+ *
+ * A view describes images [.. B) of H x W pixels, each inside a frame of
+ * (H + 2*border) x (W + 2*border) zero-bordered pixels, flattened to rows
+ *   p = (b*(H+2*border) + y+border)*(W+2*border) + x+border,
+ * preceded by `guard` rows (and followed by a tail guard inside `rows`).
+ *   layout PL: [plane][chunk][row][64 ch] (16-bit), 16-byte groups XOR-swizzled by (row & 7);
+ *              `nchunks` = 64-channel chunks per plane of the buffer, `chunk0` = first chunk
+ *              of the view; border must be 1;
+ *   layout SC: [plane][row][nchunks channels] (16-bit) row-major, channels in {4, 16, 32}.
+ * nplanes: 1 = bf16;  2 = fp16 hi + fp16 (v - hi) * 2^11 (fp32 values to ~2^-22 relative;
+ * |v| <= 65504).  The zero border must be kept zero by the caller (kernels never write it).
+ * --------------------------------------------------------------------------------- */
+#define SGTA_LAYOUT_PL 0
+#define SGTA_LAYOUT_SC 1
+typedef struct sgta_planes {
+  void* data;       /* device pointer: plane 0, chunk 0, row 0 (first guard row)        */
+  int64_t rows;     /* rows per (plane, chunk), guards included                          */
+  int32_t guard;    /* rows before padded pixel 0 of this view                           */
+  int32_t nchunks;  /* PL: chunks per plane of the buffer;  SC: channels per row         */
+  int32_t chunk0;   /* PL: first chunk of this view                                      */
+  int32_t nplanes;  /* 1 or 2                                                            */
+  int32_t layout;   /* SGTA_LAYOUT_*                                                     */
+  int32_t border;   /* zero-border width of the frame (PL: 1; SC stem input: 3)          */
+  int32_t B, H, W;  /* images of the view and their unpadded size                        */
+} sgta_planes;
+
+#define SGTA_EPI_PL 0       /* y view, layout PL, same nplanes as x (+ optional residual, act) */
+#define SGTA_EPI_SC 1       /* y view, layout SC                                               */
+#define SGTA_EPI_F32ROWS 2  /* y_f32[p*ld_f32 + o] for every padded row p (DCN offset/mask)    */
+#define SGTA_EPI_NCHW 3     /* y_f32 [B, n_valid, Ho, Wo] fp32 (heads; act may be sigmoid)     */
+#define SGTA_EPI_STEM 4     /* Cout == 32 -> SC view with 16 ch: relu(a[c]) + relu(a[16+c])    */
+
+/* rows of guard recommended before / after the frames of a W-wide map */
+int sgta_planes_guard(int W);
+/* output-channel tile the kernels use for (Cout, nplanes); -1 if unsupported */
+int sgta_planes_ntile(int Cout, int nplanes);
+/* Weight matrix Wm [Cout][Kpad] fp32 (K = (tap, channel), channel fastest, zero padded to
+ * Kpad % 64 == 0; Cout % 16 == 0) -> packed SWIZZLE_128B tiles, hi/lo split if nplanes == 2. */
+int64_t sgta_planes_wpack_bytes(int Cout, int Kpad, int nplanes);
+int sgta_planes_pack_weight(const void* wm_f32, void* wpack, int Cout, int Kpad, int nplanes,
+                            void* stream);
+/* Convolution on a PL input (dla.py:41-69, :157-175, :212-216; base_model.py:121-135):
+ * ksize 1 or 3 (pad = ksize/2), stride 1 (TMA shift-GEMM) or 3x3 stride 2 (gather-GEMM).
+ * y = act(scale*conv + shift (+ res)); scale/shift fold bias and eval BatchNorm. */
+int sgta_planes_conv(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
+                     const sgta_planes* res, const sgta_planes* y, void* y_f32, int64_t ld_f32,
+                     int Cin, int Cout, int ksize, int stride, int act, int epi, int n_valid,
+                     void* stream);
+/* Convolution on an SC input (stems dla.py:241-270, level0/1 :302-312, level2 entry).  K block
+ * kb (64 wide = 128 bytes per output pixel) is made of 8/seg_groups segments; segment j is a
+ * run of seg_groups*16 contiguous bytes starting at input row
+ *   anchor(b,oy,ox) + seg_off[kb*2 + j],  anchor = frame(b) + (oy*stride)*(W+2*border) + ox*stride
+ * (HOST table; the caller builds the matching weight matrix). */
+int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
+                        const sgta_planes* y, int Cout, int stride, int Ho, int Wo, int nkb,
+                        int seg_groups, const int* seg_off, int act, int epi, void* stream);
+/* DeformConv main GEMM (dla.py:538-550): DCNv2 3x3/s1/p1/d1/dg1 + folded bias/BN (+ReLU).
+ * offset_mask: fp32 [padded rows][32] raw conv_offset_mask output (SGTA_EPI_F32ROWS). */
+int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, const void* wpack,
+                    const void* scale, const void* shift, const sgta_planes* y, int Cin, int Cout,
+                    int relu, void* stream);
+/* layout converters / memory-bound ops (planes_ops.cu); C, c_off multiples of 8 */
+int sgta_planes_from_nchw(const void* src_f32, const sgta_planes* y, int C, int c_off, void* stream);
+int sgta_planes_to_nchw(const sgta_planes* x, void* dst_f32, int C, int c_off, void* stream);
+/* img [B,3,H,W] + hm [B,1,H,W] fp32 -> images [b_off, b_off+B) of an SC view with 4 channels */
+int sgta_planes_pack_stem(const void* img_f32, const void* hm_f32, const sgta_planes* y, int b_off,
+                          int B, void* stream);
+/* nn.MaxPool2d(2, 2) of Tree.downsample (dla.py:209-210) */
+int sgta_planes_maxpool2(const sgta_planes* x, int xc_off, const sgta_planes* y, int yc_off, int C,
+                         void* stream);
+/* IDAUp: y = ConvTranspose2d(C,C,2f,stride=f,padding=f/2,groups=C)(x) + skip (dla.py:561-577) */
+int sgta_planes_upsample_add(const sgta_planes* x, const void* w_up, const sgta_planes* skip,
+                             const sgta_planes* y, int C, int f, void* stream);
+/* rows[b,t,:] (fp32 [B,n,C]) <-> images [b_off, b_off+B) of the view at ids[b,t] = y*W + x;
+ * write-back with duplicate ids: the HIGHEST t wins (dla.py:915-968, :1006-1018) */
+int sgta_planes_gather_tokens(const sgta_planes* x, int b_off, const void* ids, void* rows, int B,
+                              int C, int n, void* stream);
+int sgta_planes_scatter_tokens(const sgta_planes* x, int b_off, const void* ids, const void* rows,
+                               int B, int C, int n, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Structure-prior temporal attention (dla.py:868-887 MHCA_ein.forward core):

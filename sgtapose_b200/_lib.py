@@ -17,8 +17,33 @@ _I = _c.c_int
 _F = _c.c_float
 _L = _c.c_int64
 
+
+
+class SgtaPlanes(ctypes.Structure):
+    """struct sgta_planes (include/sgta_b200.h)."""
+    _fields_ = [("data", _c.c_void_p), ("rows", _c.c_int64), ("guard", _c.c_int32), ("nchunks", _c.c_int32),
+                ("chunk0", _c.c_int32), ("nplanes", _c.c_int32), ("layout", _c.c_int32), ("border", _c.c_int32),
+                ("B", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32)]
+
+
+_V = _c.POINTER(SgtaPlanes)
+
 # name -> (restype, argtypes); mirrors include/sgta_b200.h one to one
 SIGNATURES = {
+    "sgta_planes_guard": (_I, [_I]),
+    "sgta_planes_ntile": (_I, [_I, _I]),
+    "sgta_planes_wpack_bytes": (_c.c_int64, [_I, _I, _I]),
+    "sgta_planes_pack_weight": (_I, [_P, _P, _I, _I, _I, _P]),
+    "sgta_planes_conv": (_I, [_V, _P, _P, _P, _V, _V, _P, _L] + [_I] * 7 + [_P]),
+    "sgta_planes_conv_sc": (_I, [_V, _P, _P, _P, _V] + [_I] * 6 + [_c.POINTER(_I), _I, _I, _P]),
+    "sgta_planes_dcn": (_I, [_V, _P, _P, _P, _P, _V, _I, _I, _I, _P]),
+    "sgta_planes_from_nchw": (_I, [_P, _V, _I, _I, _P]),
+    "sgta_planes_to_nchw": (_I, [_V, _P, _I, _I, _P]),
+    "sgta_planes_pack_stem": (_I, [_P, _P, _V, _I, _I, _P]),
+    "sgta_planes_maxpool2": (_I, [_V, _I, _V, _I, _I, _P]),
+    "sgta_planes_upsample_add": (_I, [_V, _P, _V, _V, _I, _I, _P]),
+    "sgta_planes_gather_tokens": (_I, [_V, _I, _P, _P, _I, _I, _I, _P]),
+    "sgta_planes_scatter_tokens": (_I, [_V, _I, _P, _P, _I, _I, _I, _P]),
     "sgta_abi_version": (_I, []),
     "sgta_last_error": (_c.c_char_p, []),
     "sgta_launch_count": (_c.c_int64, []),

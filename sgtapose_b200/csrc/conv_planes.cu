@@ -1,0 +1,787 @@
+// Convolutions of the hot path as tcgen05 / TMEM implicit GEMMs over the zero-bordered
+// "planes" layouts of planes.cuh (reference: sgtapose/lib/model/networks/dla.py:41-69
+// BasicBlock, :157-175 Root, :212-216 project, :241-270 stems, :302-312 conv levels, :538-550
+// DeformConv; base_model.py:121-135 heads).
+//
+//   y[p, o] = act( scale[o] * sum_k A[p, k] * Wt[k, o] + shift[o] (+ residual[p, o]) )
+//
+// Two kernels share the MMA issue loop and the epilogue:
+//
+//  conv_shift_kernel  (3x3 / 1x1, stride 1, Cin % 64 == 0: ~75 % of the network's FLOPs)
+//      The A operand is never gathered.  Output rows m0..m0+127 of tap (dy,dx) read input rows
+//      m0 + dy*(W+2) + dx .. +127, and a PL buffer already IS the SWIZZLE_128B operand image,
+//      so per 64-channel chunk the TMA engine bulk-copies three row bands (one per dy, 144
+//      rows) and the three dx taps are UMMA descriptors that start one row apart inside the
+//      band.  Warp roles: 1 TMA thread, 1 MMA thread, 4 epilogue warps; persistent CTAs with a
+//      double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of i+1.
+//
+//  conv_gather_kernel (A built by 8 producer warps, 8 lanes per 128-byte row so every
+//      warp-wide load covers whole cache lines)
+//      DCN   : A[p,(tap,c)] = sigmoid(mask) * bilinear(x[:,c], p + tap + offset); the zero
+//              border of the frame implements "zero outside" (upstream DCNv2 writes the
+//              [9*Cin, H*W] column matrix to HBM and reads it back for cuBLAS);
+//      STRIDE: 3x3 stride-2 convolutions on PL inputs (one per DLA level);
+//      SMALLC: convolutions on SC inputs (C in {4,16,32}: 7x7 stems, level0, level1, level2
+//              entry), K blocks = 128-byte runs of consecutive pixels described by a table.
+//
+// NS = 1: bf16 planes, one MMA per K step.  NS = 2: fp16 hi/lo planes, three MMAs per K step
+// into two accumulators (D0 = hi*hi, D1 = hi*lo + lo*hi), y = D0 + D1 * 2^-11.
+#include "common.cuh"
+#include "planes.cuh"
+#include "umma.cuh"
+
+namespace sgta {
+using namespace umma;
+
+constexpr int TM = 128;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int G_PROD_WARPS = 8;
+constexpr int G_THREADS = (G_PROD_WARPS + 2 + 4) * 32;   // producers, B loader, MMA, 4 epilogue warps
+constexpr int S_THREADS = 6 * 32;                        // TMA, MMA, 4 epilogue warps
+
+enum { PROD_DCN = 0, PROD_STRIDE = 1, PROD_SMALLC = 2 };
+
+struct ConvP {
+  View x, res, y;
+  const float* om;
+  const unsigned char* wpack;
+  const float* scale;
+  const float* shift;
+  float* yf;
+  long long ldyf;
+  int n_valid;
+  int P;                 // output rows = B*(Ho+2)*(Wo+2)
+  int Ho, Wo;
+  int taps, KC, nkb;     // shift: taps in {1,9}; nkb = K blocks per tile
+  int NT, n_tiles, m_tiles;
+  int SA, SB, a_rows;
+  int act, epi, tmem_cols;
+  int stride;
+  int in_Wp, in_Hp;      // input frame (gather kernels)
+  int seg_groups;        // SMALLC: 16-byte groups per segment (8 or 4)
+  int seg_off[16];       // SMALLC: input row offset of segment j of K block kb at [kb*2 + j]
+  int vec8;              // SMALLC: rows are only 8-byte aligned (C = 4)
+};
+
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// one 64-wide K block: 4 K steps, NS*(NS+1)/2 MMAs each
+template <int NS>
+__device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
+                                             uint32_t tD0, uint32_t tD1, uint32_t idesc, bool first) {
+  const uint64_t ah = smem_desc_sw128(a_addr), bh = smem_desc_sw128(b_addr);
+  const uint64_t al = smem_desc_sw128(a_addr + a_plane), bl = smem_desc_sw128(b_addr + b_plane);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t acc = (first && k == 0) ? 0u : 1u;
+    mma_bf16_ss(tD0, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, acc);
+    if (NS == 2) {
+      mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, acc);
+      mma_bf16_ss(tD1, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ epilogue
+// One thread = one output row (TMEM lane).  tacc: TMEM address of D0 incl. the lane base.
+template <int NS>
+__device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row) {
+  const int NT = p.NT;
+  const int m = m0 + row;
+  const int Wp = p.Wo + 2, Hp = p.Ho + 2;
+  const int px = m % Wp, t = m / Wp, py = t % Hp, b = t / Hp;
+  const bool inP = m < p.P;
+  const bool valid = inP && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
+  if (p.epi == SGTA_EPI_STEM) {
+    // N = 32: out[c] = relu(bn_a(acc[c])) + relu(bn_b(acc[16+c])), c < 16   (dla.py:325-331)
+    uint32_t a0[16], a1[16], b0[16], b1[16];
+    tmem_ld16(tacc, a0);
+    tmem_ld16(tacc + 16, b0);
+    if (NS == 2) { tmem_ld16(tacc + NT, a1); tmem_ld16(tacc + NT + 16, b1); }
+    tmem_ld_wait();
+    if (valid) {
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float va = __uint_as_float(a0[j]), vb = __uint_as_float(b0[j]);
+        if (NS == 2) { va = fmaf(__uint_as_float(a1[j]), LO_INV, va); vb = fmaf(__uint_as_float(b1[j]), LO_INV, vb); }
+        va = fmaf(va, __ldg(p.scale + j), __ldg(p.shift + j));
+        vb = fmaf(vb, __ldg(p.scale + 16 + j), __ldg(p.shift + 16 + j));
+        o[j] = fmaxf(va, 0.f) + fmaxf(vb, 0.f);
+      }
+      float lo8[8], hi8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { lo8[j] = o[j]; hi8[j] = o[8 + j]; }
+      sc_store8<NS>(p.y, m, 0, lo8);
+      sc_store8<NS>(p.y, m, 8, hi8);
+    }
+    return;
+  }
+  for (int c0 = 0; c0 < NT; c0 += 16) {
+    uint32_t d0[16], d1[16];
+    __syncwarp();                      // tcgen05.ld is warp-collective: reconverge after the stores
+    tmem_ld16(tacc + (uint32_t)c0, d0);
+    if (NS == 2) tmem_ld16(tacc + (uint32_t)(NT + c0), d1);
+    tmem_ld_wait();
+    const int n = n0 + c0;
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v = __uint_as_float(d0[j]);
+      if (NS == 2) v = fmaf(__uint_as_float(d1[j]), LO_INV, v);
+      o[j] = fmaf(v, __ldg(p.scale + n + j), __ldg(p.shift + n + j));
+    }
+    if (p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC) {
+      if (!valid) continue;
+      if (p.res.base) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float f[8];
+          const int ch = n + 8 * h;
+          pl_load8<NS>(p.res, ch >> 6, m, (ch & 63) >> 3, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[8 * h + j] += f[j];
+        }
+      }
+      if (p.act == SGTA_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = o[8 * h + j];
+        const int ch = n + 8 * h;
+        if (p.epi == SGTA_EPI_PL) pl_store8<NS>(p.y, ch >> 6, m, (ch & 63) >> 3, f);
+        else sc_store8<NS>(p.y, m, ch, f);
+      }
+    } else if (p.epi == SGTA_EPI_F32ROWS) {
+      if (!inP) continue;
+      float4* dst = reinterpret_cast<float4*>(p.yf + (size_t)m * p.ldyf + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    } else {   // SGTA_EPI_NCHW: fp32 [B, n_valid, Ho, Wo]
+      if (!valid) continue;
+      const size_t hw = (size_t)p.Ho * p.Wo;
+      float* dst = p.yf + ((size_t)b * p.n_valid + n) * hw + (size_t)(py - 1) * p.Wo + (px - 1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (n + j < p.n_valid) {
+          float v = o[j];
+          if (p.act == SGTA_ACT_RELU) v = fmaxf(v, 0.f);
+          else if (p.act == SGTA_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+          dst[(size_t)j * hw] = v;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned char* align1024(unsigned char* p) {
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* slot, int cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, int cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// =============================================================================== shift kernel
+template <int NS>
+__global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_constant__ ConvP p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align1024(smem_raw);
+  const int NT = p.NT;
+  const uint32_t a_plane = (uint32_t)p.a_rows * 128u, a_stage = a_plane * NS;
+  const uint32_t b_plane = (uint32_t)NT * 128u, b_stage = b_plane * NS;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + (size_t)p.SA * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.SB * b_stage);
+  uint64_t *a_full = bars, *a_empty = bars + 8, *b_full = bars + 16, *b_empty = bars + 24;
+  uint64_t *acc_full = bars + 32, *acc_empty = bars + 34;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int total = p.m_tiles * p.n_tiles;
+  const int Wp = p.x.W + 2;
+  const int nb = p.taps == 9 ? 3 : 1;
+  const int ntap_b = p.taps == 9 ? 3 : 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      uint32_t ac = 0, bc = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+        for (int kc = 0; kc < p.KC; ++kc) {
+          for (int band = 0; band < nb; ++band) {
+            const long long s = (long long)p.x.guard + m0 + (p.taps == 9 ? (band - 1) * Wp - 1 : 0);
+            const long long s8 = s & ~7ll;
+            const int st = ac % p.SA;
+            mbar_wait(&a_empty[st], ((ac / p.SA) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&a_full[st], a_stage);
+#pragma unroll
+            for (int pl = 0; pl < NS; ++pl)
+              bulk_g2s(sA + (size_t)st * a_stage + pl * a_plane,
+                       p.x.base + ((((size_t)pl * p.x.nchunks + p.x.chunk0 + kc) * p.x.rows + s8) << 7), a_plane,
+                       &a_full[st]);
+            ++ac;
+            for (int dx = 0; dx < ntap_b; ++dx) {
+              const int tap = band * ntap_b + dx;
+              const int sb = bc % p.SB;
+              mbar_wait(&b_empty[sb], ((bc / p.SB) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&b_full[sb], b_stage);
+              bulk_g2s(sB + (size_t)sb * b_stage, p.wpack + ((size_t)nt * p.nkb + (size_t)tap * p.KC + kc) * b_stage,
+                       b_stage, &b_full[sb]);
+              ++bc;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+      uint32_t ac = 0, bc = 0, it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int m0 = (t / p.n_tiles) * TM;
+        const uint32_t as = it & 1u;
+        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tD0 = tmem + as * (uint32_t)(NS * NT), tD1 = tD0 + (uint32_t)NT;
+        bool first = true;
+        for (int kc = 0; kc < p.KC; ++kc) {
+          for (int band = 0; band < nb; ++band) {
+            const long long s = (long long)p.x.guard + m0 + (p.taps == 9 ? (band - 1) * Wp - 1 : 0);
+            const uint32_t off = (uint32_t)(s & 7ll);
+            const int st = ac % p.SA;
+            mbar_wait(&a_full[st], (ac / p.SA) & 1u);
+            const uint32_t a_base = smem_u32(sA + (size_t)st * a_stage);
+            for (int dx = 0; dx < ntap_b; ++dx) {
+              const int sb = bc % p.SB;
+              mbar_wait(&b_full[sb], (bc / p.SB) & 1u);
+              tc_fence_after();
+              issue_kblock<NS>(a_base + (off + (uint32_t)dx) * 128u, a_plane, smem_u32(sB + (size_t)sb * b_stage),
+                               b_plane, tD0, tD1, idesc, first);
+              first = false;
+              mma_commit(&b_empty[sb]);
+              ++bc;
+            }
+            mma_commit(&a_empty[st]);
+            ++ac;
+          }
+        }
+        mma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+      const uint32_t as = it & 1u;
+      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      tc_fence_after();
+      epilogue_tile<NS>(p, tmem + as * (uint32_t)(NS * NT) + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem, p.tmem_cols);
+}
+
+// =============================================================================== gather kernel
+template <int PROD, int NS>
+__global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_constant__ ConvP p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align1024(smem_raw);
+  const int NT = p.NT;
+  constexpr uint32_t a_plane = TM * 128u, a_bytes = a_plane * NS;
+  const uint32_t b_plane = (uint32_t)NT * 128u, b_bytes = b_plane * NS;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.SA * stage_bytes);
+  uint64_t *full = bars, *empty = bars + 8, *acc_full = bars + 16, *acc_empty = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 8; ++s) { mbar_init(&full[s], G_PROD_WARPS + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == G_PROD_WARPS + 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int total = p.m_tiles * p.n_tiles;
+  const int nkb = p.nkb;
+
+  if (warp < G_PROD_WARPS) {
+    // ================================================================== A producers
+    const int sub = lane >> 3, c8 = lane & 7;
+    const int Wpo = p.Wo + 2, Hpo = p.Ho + 2;
+    const int iWp = p.in_Wp, iHp = p.in_Hp;
+    uint32_t kc_cnt = 0;   // K blocks produced so far (ring position)
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int m0 = (t / p.n_tiles) * TM;
+      int rr[4];          // tile rows of this thread
+      int fb[4];          // input frame base row (b * iHp * iWp)
+      int oy[4], ox[4];   // clamped unpadded output coordinates
+      bool ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rr[i] = warp * 16 + i * 4 + sub;
+        const int m = m0 + rr[i];
+        const int px = m % Wpo, tq = m / Wpo, py = tq % Hpo;
+        int b = tq / Hpo;
+        ok[i] = m < p.P && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
+        b = min(b, p.x.B - 1);
+        oy[i] = min(max(py - 1, 0), p.Ho - 1);
+        ox[i] = min(max(px - 1, 0), p.Wo - 1);
+        fb[i] = b * iHp * iWp;
+      }
+      auto wait_stage = [&](uint32_t kc) -> unsigned char* {
+        const uint32_t s = kc % (uint32_t)p.SA;
+        mbar_wait(&empty[s], ((kc / (uint32_t)p.SA) & 1u) ^ 1u);
+        return smem + (size_t)s * stage_bytes;
+      };
+      auto publish = [&](uint32_t kc) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[kc % (uint32_t)p.SA]);
+      };
+
+      if (PROD == PROD_DCN) {
+        for (int tap = 0; tap < 9; ++tap) {
+          int q00[4];
+          float w00[4], w01[4], w10[4], w11[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float* om = p.om + (size_t)(m0 + rr[i]) * 32;
+            float dy = 0.f, dx = 0.f, ml = 0.f;
+            if (ok[i]) { dy = __ldg(om + 2 * tap); dx = __ldg(om + 2 * tap + 1); ml = __ldg(om + 18 + tap); }
+            // padded-frame coordinates: unpadded + 1
+            float sy = (float)(oy[i] + tap / 3) + dy;
+            float sx = (float)(ox[i] + tap % 3) + dx;
+            const bool in = ok[i] && sy > 0.f && sy < (float)(p.Ho + 1) && sx > 0.f && sx < (float)(p.Wo + 1);
+            float msk = in ? 1.f / (1.f + __expf(-ml)) : 0.f;
+            sy = in ? sy : 0.f;
+            sx = in ? sx : 0.f;
+            const float yf = floorf(sy), xf = floorf(sx);
+            const float ly = sy - yf, lx = sx - xf, hy = 1.f - ly, hx = 1.f - lx;
+            w00[i] = msk * hy * hx; w01[i] = msk * hy * lx; w10[i] = msk * ly * hx; w11[i] = msk * ly * lx;
+            q00[i] = fb[i] + (int)yf * iWp + (int)xf;
+          }
+          for (int kc = 0; kc < p.KC; ++kc, ++kc_cnt) {
+            unsigned char* sA = wait_stage(kc_cnt);
+#pragma unroll
+            for (int ih = 0; ih < 2; ++ih) {
+              uint4 v[2][4][NS];
+#pragma unroll
+              for (int ii = 0; ii < 2; ++ii) {
+                const int i = ih * 2 + ii;
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) {
+                  const long long q = (long long)q00[i] + (cn >> 1) * iWp + (cn & 1);
+#pragma unroll
+                  for (int pl = 0; pl < NS; ++pl)
+                    v[ii][cn][pl] = __ldg(reinterpret_cast<const uint4*>(p.x.base + pl_offset(p.x, pl, kc, q, c8)));
+                }
+              }
+#pragma unroll
+              for (int ii = 0; ii < 2; ++ii) {
+                const int i = ih * 2 + ii;
+                float f[4][8];
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) decode8<NS>(v[ii][cn][0], v[ii][cn][NS - 1], f[cn]);
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  o[j] = w00[i] * f[0][j] + w01[i] * f[1][j] + w10[i] * f[2][j] + w11[i] * f[3][j];
+                uint4 e0, e1;
+                encode8<NS>(o, e0, e1);
+                const uint32_t off = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
+                *reinterpret_cast<uint4*>(sA + off) = e0;
+                if (NS == 2) *reinterpret_cast<uint4*>(sA + a_plane + off) = e1;
+              }
+            }
+            publish(kc_cnt);
+          }
+        }
+      } else if (PROD == PROD_STRIDE) {
+        // 3x3, pad 1, stride s on a PL input: padded input coords of tap (ky,kx) = (oy*s+ky, ox*s+kx)
+        for (int tap = 0; tap < 9; ++tap) {
+          long long q[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            q[i] = (long long)fb[i] + (oy[i] * p.stride + tap / 3) * iWp + ox[i] * p.stride + tap % 3;
+          for (int kc = 0; kc < p.KC; ++kc, ++kc_cnt) {
+            unsigned char* sA = wait_stage(kc_cnt);
+            uint4 v[4][NS];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int pl = 0; pl < NS; ++pl)
+                v[i][pl] = __ldg(reinterpret_cast<const uint4*>(p.x.base + pl_offset(p.x, pl, kc, q[i], c8)));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t off = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
+#pragma unroll
+              for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + off) = v[i][pl];
+            }
+            publish(kc_cnt);
+          }
+        }
+      } else {
+        // SC input: group c8 of K block kb = 16 bytes at byte (anchor + seg_off)*C*2 + (c8 % g)*16
+        const int C2 = p.x.nchunks * 2;   // bytes per input row
+        long long anchor[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) anchor[i] = (long long)fb[i] + (long long)(oy[i] * p.stride) * iWp + ox[i] * p.stride;
+        const int seg = c8 / p.seg_groups, within = c8 % p.seg_groups;
+        for (int kb = 0; kb < nkb; ++kb, ++kc_cnt) {
+          unsigned char* sA = wait_stage(kc_cnt);
+          const int so = p.seg_off[kb * 2 + seg];
+          uint4 v[4][NS];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int pl = 0; pl < NS; ++pl) {
+              const unsigned char* src = p.x.base + ((size_t)pl * p.x.rows + p.x.guard + anchor[i] + so) * C2 + within * 16;
+              if (p.vec8) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(src + 8));
+                v[i][pl] = make_uint4(a.x, a.y, b.x, b.y);
+              } else {
+                v[i][pl] = __ldg(reinterpret_cast<const uint4*>(src));
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t off = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
+#pragma unroll
+            for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + off) = v[i][pl];
+          }
+          publish(kc_cnt);
+        }
+      }
+    }
+  } else if (warp == G_PROD_WARPS) {
+    // ==================================================================== B loader
+    if (lane == 0) {
+      uint32_t kc_cnt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        for (int kb = 0; kb < nkb; ++kb, ++kc_cnt) {
+          const uint32_t s = kc_cnt % (uint32_t)p.SA;
+          mbar_wait(&empty[s], ((kc_cnt / (uint32_t)p.SA) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full[s], b_bytes);
+          bulk_g2s(smem + (size_t)s * stage_bytes + a_bytes, p.wpack + ((size_t)nt * nkb + kb) * b_bytes, b_bytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp == G_PROD_WARPS + 1) {
+    // ==================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+      uint32_t kc_cnt = 0, it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const uint32_t as = it & 1u;
+        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tD0 = tmem + as * (uint32_t)(NS * NT), tD1 = tD0 + (uint32_t)NT;
+        for (int kb = 0; kb < nkb; ++kb, ++kc_cnt) {
+          const uint32_t s = kc_cnt % (uint32_t)p.SA;
+          mbar_wait(&full[s], (kc_cnt / (uint32_t)p.SA) & 1u);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes);
+          issue_kblock<NS>(a0, a_plane, a0 + a_bytes, b_plane, tD0, tD1, idesc, kb == 0);
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ==================================================================== epilogue warps
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+      const uint32_t as = it & 1u;
+      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      tc_fence_after();
+      epilogue_tile<NS>(p, tmem + as * (uint32_t)(NS * NT) + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == G_PROD_WARPS + 1) tmem_dealloc_dyn(tmem, p.tmem_cols);
+}
+
+// =============================================================================== weights
+// Wm [Cout][Kpad] fp32 -> wpack[n tile][K block][plane][NT x 64 SWIZZLE_128B image]
+__global__ void pack_weight_planes_kernel(const float* __restrict__ wm, unsigned char* __restrict__ wpack, int Cout,
+                                          int Kpad, int NT, int NS) {
+  const int nkb = Kpad / 64;
+  const long long total = (long long)Cout * Kpad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % Kpad), n = (int)(e / Kpad);
+    const int kb = k / 64, kk = k % 64, t = n / NT, row = n % NT;
+    const float v = wm[e];
+    const size_t base = ((size_t)t * nkb + kb) * (size_t)NT * 128 * NS;
+    const size_t off = sw128_offset(row, kk / 8) + (kk % 8) * 2;
+    if (NS == 2) {
+      const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+      const __half hi = __float2half_rn(c);
+      *reinterpret_cast<__half*>(wpack + base + off) = hi;
+      *reinterpret_cast<__half*>(wpack + base + (size_t)NT * 128 + off) = __float2half_rn((c - __half2float(hi)) * LO_SCALE);
+    } else {
+      *reinterpret_cast<__nv_bfloat16*>(wpack + base + off) = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+static int pick_ntile(int Cout, int NS) {
+  if (Cout < 16 || Cout % 16) return -1;
+  const int cap = NS == 2 ? 128 : 256;
+  int nt = Cout;
+  if (nt > cap) {
+    nt = cap;
+    while (Cout % nt) nt -= 16;
+  }
+  return nt;
+}
+static int tmem_cols_for(int NT, int NS) {
+  int need = 2 * NS * NT, c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+template <int NS>
+static int launch_shift(ConvP& p, cudaStream_t st) {
+  const int a_stage = p.a_rows * 128 * NS, b_stage = p.NT * 128 * NS;
+  const int fixed = 1024 + 512;
+  int SB = 4, SA = 3;
+  while (SB > 2 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SB;
+  while (SA > 1 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SA;
+  if (SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) { set_error("conv_shift: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
+  // spend what is left on deeper rings
+  while (SA < 6 && (SA + 1) * a_stage + SB * b_stage + fixed <= SMEM_LIMIT && SA <= SB) ++SA;
+  while (SB < 8 && SA * a_stage + (SB + 1) * b_stage + fixed <= SMEM_LIMIT) ++SB;
+  p.SA = SA; p.SB = SB;
+  const int smem = SA * a_stage + SB * b_stage + fixed;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sms ? total : sms;
+  cudaFuncSetAttribute(conv_shift_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  conv_shift_kernel<NS><<<grid, S_THREADS, smem, st>>>(p);
+  return check_launch("conv_shift_kernel");
+}
+
+template <int PROD, int NS>
+static int launch_gather(ConvP& p, cudaStream_t st) {
+  const int stage = (TM * 128 + p.NT * 128) * NS;
+  const int fixed = 1024 + 512;
+  int SA = (SMEM_LIMIT - fixed) / stage;
+  if (SA > 6) SA = 6;
+  if (SA < 2) { set_error("conv_gather: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
+  p.SA = SA; p.SB = 0;
+  const int smem = SA * stage + fixed;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sms ? total : sms;
+  cudaFuncSetAttribute(conv_gather_kernel<PROD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  conv_gather_kernel<PROD, NS><<<grid, G_THREADS, smem, st>>>(p);
+  return check_launch("conv_gather_kernel");
+}
+
+static bool view_ok(const sgta_planes* v, int layout) {
+  return v && v->data && v->layout == layout && (v->nplanes == 1 || v->nplanes == 2) && v->B > 0 && v->H > 0 &&
+         v->W > 0 && v->guard >= 0 && v->rows >= (int64_t)v->guard + (int64_t)v->B * (v->H + 2 * v->border) * (v->W + 2 * v->border);
+}
+
+}  // namespace sgta
+
+using namespace sgta;
+
+extern "C" int sgta_planes_ntile(int Cout, int nplanes) { return pick_ntile(Cout, nplanes); }
+
+extern "C" int sgta_planes_guard(int W) { return ((W + 2) * 8 + 160 + 7) & ~7; }
+
+extern "C" int64_t sgta_planes_wpack_bytes(int Cout, int Kpad, int nplanes) {
+  if (pick_ntile(Cout, nplanes) < 0 || Kpad <= 0 || Kpad % 64) return -1;
+  return (int64_t)Cout * Kpad * 2 * nplanes;
+}
+
+extern "C" int sgta_planes_pack_weight(const void* wm_f32, void* wpack, int Cout, int Kpad, int nplanes, void* stream) {
+  SGTA_REQUIRE(wm_f32 && wpack, "sgta_planes_pack_weight: null pointer");
+  SGTA_REQUIRE(nplanes == 1 || nplanes == 2, "sgta_planes_pack_weight: nplanes must be 1 or 2");
+  const int nt = pick_ntile(Cout, nplanes);
+  SGTA_REQUIRE(nt > 0 && Kpad > 0 && Kpad % 64 == 0, "sgta_planes_pack_weight: need Cout %% 16 == 0 and Kpad %% 64 == 0 (got %d, %d)", Cout, Kpad);
+  const long long total = (long long)Cout * Kpad;
+  const int blocks = cdiv(total, 256) > 2368 ? 2368 : cdiv(total, 256);
+  pack_weight_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)wm_f32, (unsigned char*)wpack, Cout, Kpad, nt, nplanes);
+  return check_launch("pack_weight_planes_kernel");
+}
+
+static int fill_output(ConvP& p, const sgta_planes* y, void* y_f32, int64_t ld_f32, int Cout, int epi, int n_valid,
+                       int B, int Ho, int Wo, int nplanes, const char* who) {
+  p.epi = epi;
+  p.n_valid = n_valid > 0 ? n_valid : Cout;
+  if (epi == SGTA_EPI_PL) {
+    SGTA_REQUIRE(view_ok(y, SGTA_LAYOUT_PL) && y->nplanes == nplanes && y->border == 1, "%s: bad PL output view", who);
+    SGTA_REQUIRE(Cout % 64 == 0 && y->chunk0 + Cout / 64 <= y->nchunks, "%s: PL output needs Cout %% 64 == 0 inside the buffer", who);
+  } else if (epi == SGTA_EPI_SC || epi == SGTA_EPI_STEM) {
+    SGTA_REQUIRE(view_ok(y, SGTA_LAYOUT_SC) && y->nplanes == nplanes && y->border == 1, "%s: bad SC output view", who);
+    SGTA_REQUIRE(epi == SGTA_EPI_STEM ? (Cout == 32 && y->nchunks == 16) : y->nchunks == Cout, "%s: SC output channel mismatch", who);
+  } else {
+    SGTA_REQUIRE(epi == SGTA_EPI_F32ROWS || epi == SGTA_EPI_NCHW, "%s: bad epilogue", who);
+    SGTA_REQUIRE(y_f32 && (epi == SGTA_EPI_NCHW || ld_f32 >= Cout), "%s: bad fp32 output", who);
+  }
+  if (epi == SGTA_EPI_PL || epi == SGTA_EPI_SC || epi == SGTA_EPI_STEM) {
+    SGTA_REQUIRE(y->B == B && y->H == Ho && y->W == Wo, "%s: output geometry mismatch", who);
+    p.y = make_view(y);
+  }
+  p.yf = (float*)y_f32;
+  p.ldyf = ld_f32;
+  return SGTA_OK;
+}
+
+extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
+                                const sgta_planes* res, const sgta_planes* y, void* y_f32, int64_t ld_f32, int Cin,
+                                int Cout, int ksize, int stride, int act, int epi, int n_valid, void* stream) {
+  SGTA_REQUIRE(x && wpack && scale && shift, "sgta_planes_conv: null pointer");
+  SGTA_REQUIRE(x->nplanes == 1 || x->nplanes == 2, "sgta_planes_conv: nplanes must be 1 or 2");
+  const int NS = x->nplanes;
+  const int NT = pick_ntile(Cout, NS);
+  SGTA_REQUIRE(NT > 0, "sgta_planes_conv: need Cout %% 16 == 0 (got %d)", Cout);
+  SGTA_REQUIRE(stride == 1 || stride == 2, "sgta_planes_conv: stride must be 1 or 2");
+  ConvP p{};
+  p.x = make_view(x);
+  p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
+  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; p.tmem_cols = tmem_cols_for(NT, NS);
+  const int pad = ksize / 2;
+  const int Ho = (x->H + 2 * pad - ksize) / stride + 1, Wo = (x->W + 2 * pad - ksize) / stride + 1;
+  SGTA_REQUIRE(Ho > 0 && Wo > 0, "sgta_planes_conv: empty output");
+  const long long P = (long long)x->B * (Ho + 2) * (Wo + 2);
+  SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv: too many pixels");
+  p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.m_tiles = cdiv(P, TM);
+  int rc = fill_output(p, y, y_f32, ld_f32, Cout, epi, n_valid, x->B, Ho, Wo, NS, "sgta_planes_conv");
+  if (rc) return rc;
+  if (res) {
+    SGTA_REQUIRE(view_ok(res, SGTA_LAYOUT_PL) && res->nplanes == NS && res->B == x->B && res->H == Ho && res->W == Wo &&
+                 res->border == 1 && epi == SGTA_EPI_PL, "sgta_planes_conv: bad residual view");
+    p.res = make_view(res);
+  }
+  p.in_Wp = x->W + 2 * x->border; p.in_Hp = x->H + 2 * x->border;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x->layout == SGTA_LAYOUT_PL) {
+    SGTA_REQUIRE(view_ok(x, SGTA_LAYOUT_PL) && x->border == 1, "sgta_planes_conv: bad PL input view");
+    SGTA_REQUIRE(Cin % 64 == 0 && x->chunk0 + Cin / 64 <= x->nchunks, "sgta_planes_conv: PL input needs Cin %% 64 == 0 inside the buffer");
+    p.KC = Cin / 64;
+    if (stride == 1) {
+      SGTA_REQUIRE(ksize == 1 || ksize == 3, "sgta_planes_conv: PL stride-1 kernels are 1x1 or 3x3");
+      p.taps = ksize * ksize; p.nkb = p.taps * p.KC; p.a_rows = ksize == 3 ? 144 : 136;
+      const int Wp = x->W + 2;
+      SGTA_REQUIRE(x->guard >= Wp + 1 + 8 && x->rows >= (int64_t)x->guard + (int64_t)p.m_tiles * TM + Wp + 16 + 8,
+                   "sgta_planes_conv: input guard rows too small for the halo");
+      return NS == 2 ? launch_shift<2>(p, st) : launch_shift<1>(p, st);
+    }
+    SGTA_REQUIRE(ksize == 3, "sgta_planes_conv: PL strided kernels are 3x3");
+    p.taps = 9; p.nkb = 9 * p.KC;
+    return NS == 2 ? launch_gather<PROD_STRIDE, 2>(p, st) : launch_gather<PROD_STRIDE, 1>(p, st);
+  }
+  // SC input: K blocks described by the caller through sgta_planes_conv_sc
+  set_error("sgta_planes_conv: SC inputs go through sgta_planes_conv_sc");
+  return SGTA_EINVAL;
+}
+
+extern "C" int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
+                                   const sgta_planes* y, int Cout, int stride, int Ho, int Wo, int nkb,
+                                   int seg_groups, const int* seg_off /*HOST [nkb*2]*/, int act, int epi, void* stream) {
+  SGTA_REQUIRE(x && wpack && scale && shift && y && seg_off, "sgta_planes_conv_sc: null pointer");
+  SGTA_REQUIRE(view_ok(x, SGTA_LAYOUT_SC), "sgta_planes_conv_sc: bad SC input view");
+  const int NS = x->nplanes, C = x->nchunks;
+  SGTA_REQUIRE(C == 4 || C == 16 || C == 32, "sgta_planes_conv_sc: C must be 4, 16 or 32 (got %d)", C);
+  SGTA_REQUIRE(nkb >= 1 && nkb <= 8 && (seg_groups == 8 || seg_groups == 4), "sgta_planes_conv_sc: bad K-block table");
+  const int NT = pick_ntile(Cout, NS);
+  SGTA_REQUIRE(NT > 0, "sgta_planes_conv_sc: need Cout %% 16 == 0 (got %d)", Cout);
+  ConvP p{};
+  p.x = make_view(x);
+  p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
+  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; p.tmem_cols = tmem_cols_for(NT, NS);
+  const long long P = (long long)x->B * (Ho + 2) * (Wo + 2);
+  SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv_sc: too many pixels");
+  p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.m_tiles = cdiv(P, TM);
+  int rc = fill_output(p, y, nullptr, 0, Cout, epi, 0, x->B, Ho, Wo, NS, "sgta_planes_conv_sc");
+  if (rc) return rc;
+  p.in_Wp = x->W + 2 * x->border; p.in_Hp = x->H + 2 * x->border;
+  p.nkb = nkb; p.seg_groups = seg_groups; p.vec8 = C == 4;
+  for (int i = 0; i < nkb * 2; ++i) p.seg_off[i] = seg_off[i];
+  cudaStream_t st = (cudaStream_t)stream;
+  return NS == 2 ? launch_gather<PROD_SMALLC, 2>(p, st) : launch_gather<PROD_SMALLC, 1>(p, st);
+}
+
+extern "C" int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, const void* wpack, const void* scale,
+                               const void* shift, const sgta_planes* y, int Cin, int Cout, int relu, void* stream) {
+  SGTA_REQUIRE(x && offset_mask && wpack && scale && shift && y, "sgta_planes_dcn: null pointer");
+  SGTA_REQUIRE(view_ok(x, SGTA_LAYOUT_PL) && x->border == 1, "sgta_planes_dcn: bad PL input view");
+  const int NS = x->nplanes;
+  SGTA_REQUIRE(Cin % 64 == 0 && x->chunk0 + Cin / 64 <= x->nchunks, "sgta_planes_dcn: need Cin %% 64 == 0 inside the buffer");
+  const int NT = pick_ntile(Cout, NS);
+  SGTA_REQUIRE(NT > 0 && Cout % 64 == 0, "sgta_planes_dcn: need Cout %% 64 == 0 (got %d)", Cout);
+  ConvP p{};
+  p.x = make_view(x);
+  p.om = (const float*)offset_mask;
+  p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
+  p.act = relu ? SGTA_ACT_RELU : SGTA_ACT_NONE; p.stride = 1; p.NT = NT; p.n_tiles = Cout / NT;
+  p.tmem_cols = tmem_cols_for(NT, NS);
+  const long long P = (long long)x->B * (x->H + 2) * (x->W + 2);
+  SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_dcn: too many pixels");
+  p.P = (int)P; p.Ho = x->H; p.Wo = x->W; p.m_tiles = cdiv(P, TM);
+  int rc = fill_output(p, y, nullptr, 0, Cout, SGTA_EPI_PL, 0, x->B, x->H, x->W, NS, "sgta_planes_dcn");
+  if (rc) return rc;
+  p.in_Wp = x->W + 2; p.in_Hp = x->H + 2;
+  p.KC = Cin / 64; p.taps = 9; p.nkb = 9 * p.KC;
+  cudaStream_t st = (cudaStream_t)stream;
+  return NS == 2 ? launch_gather<PROD_DCN, 2>(p, st) : launch_gather<PROD_DCN, 1>(p, st);
+}

@@ -1,0 +1,278 @@
+// Memory-bound operators on the "planes" layouts (planes.cuh): converters at the module
+// boundary (the reference is NCHW fp32), the stem input packer, 2x2 max-pool
+// (dla.py:209-210), the depth-wise ConvTranspose2d up-sampler fused with the IDAUp skip add
+// (dla.py:561-577) and the prior-guided token gather / deterministic write-back
+// (dla.py:915-968, :1006-1018).  One thread moves one 16-byte group (8 channels) per plane.
+#include "common.cuh"
+#include "planes.cuh"
+
+namespace sgta {
+
+__device__ __forceinline__ long long frame_row(const View& v, int b, int y, int x) {   // unpadded (y,x)
+  const int Wp = v.W + 2, Hp = v.H + 2;
+  return ((long long)b * Hp + (y + 1)) * Wp + (x + 1);
+}
+
+template <int NS>
+__device__ __forceinline__ void load8(const View& v, long long p, int c, float (&f)[8]) {
+  if (v.layout == SGTA_LAYOUT_PL) pl_load8<NS>(v, c >> 6, p, (c & 63) >> 3, f);
+  else sc_load8<NS>(v, p, c, f);
+}
+template <int NS>
+__device__ __forceinline__ void store8(const View& v, long long p, int c, const float (&f)[8]) {
+  if (v.layout == SGTA_LAYOUT_PL) pl_store8<NS>(v, c >> 6, p, (c & 63) >> 3, f);
+  else sc_store8<NS>(v, p, c, f);
+}
+
+// ---- NCHW fp32 <-> planes -------------------------------------------------------------------
+template <int NS>
+__global__ void pl_from_nchw_kernel(const float* __restrict__ src, View y, int C, int c_off, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int HW = y.H * y.W;
+  const int pix = (int)(e % HW);
+  const long long r = e / HW;
+  const int g = (int)(r % (C / 8)), b = (int)(r / (C / 8));
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __ldg(src + ((long long)b * C + g * 8 + j) * HW + pix);
+  store8<NS>(y, frame_row(y, b, pix / y.W, pix % y.W), c_off + g * 8, f);
+}
+template <int NS>
+__global__ void pl_to_nchw_kernel(View x, float* __restrict__ dst, int C, int c_off, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int HW = x.H * x.W;
+  const int pix = (int)(e % HW);
+  const long long r = e / HW;
+  const int g = (int)(r % (C / 8)), b = (int)(r / (C / 8));
+  float f[8];
+  load8<NS>(x, frame_row(x, b, pix / x.W, pix % x.W), c_off + g * 8, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[((long long)b * C + g * 8 + j) * HW + pix] = f[j];
+}
+
+// img [B,3,H,W] + hm [B,1,H,W] fp32 -> SC view with C = 4 and a 3-pixel zero border (7x7 stems,
+// dla.py:241-270), images [b_off, b_off+B) of the view
+template <int NS>
+__global__ void pl_pack_stem_kernel(const float* __restrict__ img, const float* __restrict__ hm, View y, int b_off,
+                                 int B, int border, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int HW = y.H * y.W;
+  const int pix = (int)(e % HW), b = (int)(e / HW);
+  const int Wp = y.W + 2 * border, Hp = y.H + 2 * border;
+  const long long row = ((long long)(b + b_off) * Hp + pix / y.W + border) * Wp + pix % y.W + border;
+  const float v0 = __ldg(img + ((long long)b * 3 + 0) * HW + pix), v1 = __ldg(img + ((long long)b * 3 + 1) * HW + pix);
+  const float v2 = __ldg(img + ((long long)b * 3 + 2) * HW + pix), v3 = __ldg(hm + (long long)b * HW + pix);
+  if (NS == 2) {
+    uint32_t h0, l0, h1, l1;
+    split2(v0, v1, h0, l0);
+    split2(v2, v3, h1, l1);
+    *reinterpret_cast<uint2*>(y.base + sc_offset(y, 0, row, 0)) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(y.base + sc_offset(y, 1, row, 0)) = make_uint2(l0, l1);
+  } else {
+    *reinterpret_cast<uint2*>(y.base + sc_offset(y, 0, row, 0)) = make_uint2(pack_b2(v0, v1), pack_b2(v2, v3));
+  }
+}
+
+// ---- 2x2 / stride-2 max-pool ------------------------------------------------------------------
+template <int NS>
+__global__ void pl_maxpool2_kernel(View x, View y, int C, int xc_off, int yc_off, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = C / 8;
+  const int g = (int)(e % G);
+  long long r = e / G;
+  const int ox = (int)(r % y.W); r /= y.W;
+  const int oy = (int)(r % y.H), b = (int)(r / y.H);
+  float m[8], f[8];
+  const long long p00 = frame_row(x, b, 2 * oy, 2 * ox);
+  const int Wp = x.W + 2;
+  load8<NS>(x, p00, xc_off + g * 8, m);
+  const long long ps[3] = {p00 + 1, p00 + Wp, p00 + Wp + 1};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    load8<NS>(x, ps[k], xc_off + g * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+  }
+  store8<NS>(y, frame_row(y, b, oy, ox), yc_off + g * 8, m);
+}
+
+// ---- y = ConvTranspose2d(C,C,2f,stride f,pad f/2,groups C)(x) + skip ---------------------------
+template <int NS>
+__global__ void pl_upsample_add_kernel(View x, const float* __restrict__ w, View skip, int has_skip, View y, int C,
+                                    int f, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = C / 8;
+  const int g = (int)(e % G);
+  long long r = e / G;
+  const int ox = (int)(r % y.W); r /= y.W;
+  const int oy = (int)(r % y.H), b = (int)(r / y.H);
+  const int k = 2 * f, pad = f / 2;
+  float acc[8];
+  const long long po = frame_row(y, b, oy, ox);
+  if (has_skip) load8<NS>(skip, po, g * 8, acc);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  }
+  const int iy_hi = (oy + pad) / f, ix_hi = (ox + pad) / f;
+  for (int iy = iy_hi; iy >= 0 && iy > iy_hi - 2; --iy) {
+    const int ky = oy + pad - iy * f;
+    if (ky >= k || iy >= x.H) continue;
+    for (int ix = ix_hi; ix >= 0 && ix > ix_hi - 2; --ix) {
+      const int kx = ox + pad - ix * f;
+      if (kx >= k || ix >= x.W) continue;
+      float v[8];
+      load8<NS>(x, frame_row(x, b, iy, ix), g * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], __ldg(w + ((long long)(g * 8 + j) * k + ky) * k + kx), acc[j]);
+    }
+  }
+  store8<NS>(y, po, g * 8, acc);
+}
+
+// ---- tokens -----------------------------------------------------------------------------------
+// rows[b,t,:] = feats[b, :, ids[b,t]]  (ids = y*W + x in the unpadded map); images
+// [b_off, b_off+B) of the view
+template <int NS>
+__global__ void pl_gather_tokens_kernel(View x, int b_off, const long long* __restrict__ ids, float* __restrict__ rows,
+                                     int C, int n, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int G = C / 8;
+  const int g = (int)(e % G);
+  const long long bt = e / G;
+  const int b = (int)(bt / n);
+  const long long id = ids[bt];
+  float f[8];
+  load8<NS>(x, frame_row(x, b + b_off, (int)(id / x.W), (int)(id % x.W)), g * 8, f);
+  float4* dst = reinterpret_cast<float4*>(rows + bt * C + g * 8);
+  dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+  dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// One CTA per sample; token t writes iff no later token carries the same id (highest token
+// index wins: deterministic, == sequential index_put_).
+template <int NS>
+__global__ void __launch_bounds__(256)
+pl_scatter_tokens_kernel(View x, int b_off, const long long* __restrict__ ids, const float* __restrict__ rows, int C, int n) {
+  extern __shared__ int s_ids[];
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) s_ids[t] = (int)ids[(long long)b * n + t];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int G = C / 8;
+  for (int t = warp; t < n; t += nw) {
+    const int id = s_ids[t];
+    bool dup = false;
+    for (int u = t + 1 + lane; u < n; u += 32) dup |= (s_ids[u] == id);
+    if (__any_sync(0xffffffffu, dup)) continue;
+    const long long p = frame_row(x, b + b_off, id / x.W, id % x.W);
+    for (int g = lane; g < G; g += 32) {
+      const float4* src = reinterpret_cast<const float4*>(rows + ((long long)b * n + t) * C + g * 8);
+      const float4 a = __ldg(src), c = __ldg(src + 1);
+      const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      store8<NS>(x, p, g * 8, f);
+    }
+  }
+}
+
+static bool geom_ok(const sgta_planes* v) {
+  return v && v->data && (v->nplanes == 1 || v->nplanes == 2) && v->B > 0 && v->H > 0 && v->W > 0 &&
+         (v->layout == SGTA_LAYOUT_PL || v->layout == SGTA_LAYOUT_SC) &&
+         v->rows >= (int64_t)v->guard + (int64_t)v->B * (v->H + 2 * v->border) * (v->W + 2 * v->border);
+}
+static bool chan_ok(const sgta_planes* v, int c_off, int C) {
+  if (C <= 0 || C % 8 || c_off % 8 || c_off < 0) return false;
+  if (v->layout == SGTA_LAYOUT_PL) return (long long)v->chunk0 * 64 + c_off + C <= (long long)v->nchunks * 64;
+  return c_off + C <= v->nchunks;
+}
+
+}  // namespace sgta
+
+using namespace sgta;
+
+#define NS_DISPATCH(ns, ...)              \
+  if ((ns) == 2) { constexpr int NS = 2; __VA_ARGS__; } \
+  else { constexpr int NS = 1; __VA_ARGS__; }
+
+extern "C" int sgta_planes_from_nchw(const void* src_f32, const sgta_planes* y, int C, int c_off, void* stream) {
+  SGTA_REQUIRE(src_f32 && geom_ok(y) && y->border == 1 && chan_ok(y, c_off, C), "sgta_planes_from_nchw: bad arguments");
+  const long long total = (long long)y->B * (C / 8) * y->H * y->W;
+  View v = make_view(y);
+  NS_DISPATCH(y->nplanes, (pl_from_nchw_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)src_f32, v, C, c_off, total)));
+  return check_launch("pl_from_nchw_kernel");
+}
+
+extern "C" int sgta_planes_to_nchw(const sgta_planes* x, void* dst_f32, int C, int c_off, void* stream) {
+  SGTA_REQUIRE(dst_f32 && geom_ok(x) && x->border == 1 && chan_ok(x, c_off, C), "sgta_planes_to_nchw: bad arguments");
+  const long long total = (long long)x->B * (C / 8) * x->H * x->W;
+  View v = make_view(x);
+  NS_DISPATCH(x->nplanes, (pl_to_nchw_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(v, (float*)dst_f32, C, c_off, total)));
+  return check_launch("pl_to_nchw_kernel");
+}
+
+extern "C" int sgta_planes_pack_stem(const void* img_f32, const void* hm_f32, const sgta_planes* y, int b_off, int B,
+                                     void* stream) {
+  SGTA_REQUIRE(img_f32 && hm_f32 && geom_ok(y) && y->layout == SGTA_LAYOUT_SC && y->nchunks == 4 && y->border >= 1 &&
+               b_off >= 0 && B > 0 && b_off + B <= y->B, "sgta_planes_pack_stem: bad arguments");
+  const long long total = (long long)B * y->H * y->W;
+  View v = make_view(y);
+  NS_DISPATCH(y->nplanes, (pl_pack_stem_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const float*)img_f32, (const float*)hm_f32, v, b_off, B, y->border, total)));
+  return check_launch("pl_pack_stem_kernel");
+}
+
+extern "C" int sgta_planes_maxpool2(const sgta_planes* x, int xc_off, const sgta_planes* y, int yc_off, int C, void* stream) {
+  SGTA_REQUIRE(geom_ok(x) && geom_ok(y) && x->border == 1 && y->border == 1 && x->nplanes == y->nplanes &&
+               x->B == y->B && x->H == 2 * y->H && x->W == 2 * y->W && chan_ok(x, xc_off, C) && chan_ok(y, yc_off, C),
+               "sgta_planes_maxpool2: bad arguments");
+  const long long total = (long long)y->B * y->H * y->W * (C / 8);
+  View vx = make_view(x), vy = make_view(y);
+  NS_DISPATCH(x->nplanes, (pl_maxpool2_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, C, xc_off, yc_off, total)));
+  return check_launch("pl_maxpool2_kernel");
+}
+
+extern "C" int sgta_planes_upsample_add(const sgta_planes* x, const void* w_up, const sgta_planes* skip,
+                                        const sgta_planes* y, int C, int f, void* stream) {
+  SGTA_REQUIRE(geom_ok(x) && geom_ok(y) && w_up && f >= 1 && x->border == 1 && y->border == 1 &&
+               x->nplanes == y->nplanes && x->B == y->B && y->H == x->H * f && y->W == x->W * f &&
+               chan_ok(x, 0, C) && chan_ok(y, 0, C), "sgta_planes_upsample_add: bad arguments");
+  if (skip)
+    SGTA_REQUIRE(geom_ok(skip) && skip->border == 1 && skip->nplanes == y->nplanes && skip->B == y->B &&
+                 skip->H == y->H && skip->W == y->W && chan_ok(skip, 0, C), "sgta_planes_upsample_add: bad skip view");
+  const long long total = (long long)y->B * y->H * y->W * (C / 8);
+  View vx = make_view(x), vy = make_view(y), vs = make_view(skip);
+  NS_DISPATCH(x->nplanes, (pl_upsample_add_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              vx, (const float*)w_up, vs, skip != nullptr, vy, C, f, total)));
+  return check_launch("pl_upsample_add_kernel");
+}
+
+extern "C" int sgta_planes_gather_tokens(const sgta_planes* x, int b_off, const void* ids, void* rows, int B, int C,
+                                         int n, void* stream) {
+  SGTA_REQUIRE(geom_ok(x) && x->border == 1 && ids && rows && B > 0 && n > 0 && b_off >= 0 && b_off + B <= x->B &&
+               chan_ok(x, 0, C), "sgta_planes_gather_tokens: bad arguments");
+  const long long total = (long long)B * n * (C / 8);
+  View v = make_view(x);
+  NS_DISPATCH(x->nplanes, (pl_gather_tokens_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              v, b_off, (const long long*)ids, (float*)rows, C, n, total)));
+  return check_launch("pl_gather_tokens_kernel");
+}
+
+extern "C" int sgta_planes_scatter_tokens(const sgta_planes* x, int b_off, const void* ids, const void* rows, int B,
+                                          int C, int n, void* stream) {
+  SGTA_REQUIRE(geom_ok(x) && x->border == 1 && ids && rows && B > 0 && n > 0 && n <= 48 * 1024 && b_off >= 0 &&
+               b_off + B <= x->B && chan_ok(x, 0, C), "sgta_planes_scatter_tokens: bad arguments");
+  const size_t smem = sizeof(int) * n;
+  View v = make_view(x);
+  NS_DISPATCH(x->nplanes, {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(pl_scatter_tokens_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pl_scatter_tokens_kernel<NS><<<B, 256, smem, (cudaStream_t)stream>>>(v, b_off, (const long long*)ids, (const float*)rows, C, n);
+  });
+  return check_launch("pl_scatter_tokens_kernel");
+}
