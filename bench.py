@@ -284,7 +284,7 @@ def time_dcn_kernels(fn):
     orig = _lib.call
 
     def timed(name, *a):
-        if name.startswith("sgta_dcn_forward"):
+        if name in ("sgta_planes_dcn", "sgta_dcn_forward", "sgta_dcn_forward_nhwc"):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             orig(name, *a)

@@ -56,6 +56,8 @@ struct ConvP {
   int NT, n_tiles, m_tiles;
   int SA, SB, a_rows;
   int act, epi, tmem_cols;
+  int acc_r;             // D0 accumulators per stage (k steps rotate over them: shorter fp32 chains)
+  int acc_stages;        // TMEM accumulator stages (2 = epilogue overlaps the next tile)
   int stride;
   int in_Wp, in_Hp;      // input frame (gather kernels)
   int seg_groups;        // SMALLC: 16-byte groups per segment (8 or 4)
@@ -77,24 +79,51 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
-// one 64-wide K block: 4 K steps, NS*(NS+1)/2 MMAs each
+// one 64-wide K block: 4 K steps, NS*(NS+1)/2 MMAs each.  tacc = [D0_0 .. D0_{R-1}, D1], NT columns
+// each.  The tensor core TRUNCATES when it adds a K=16 dot product into the fp32 accumulator
+// (measured: -2.7e-5 relative on an all-positive K=4608 sum), so in the fp32-parity mode the hi*hi
+// products rotate over R accumulators that the epilogue adds in round-to-nearest fp32.
 template <int NS>
 __device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
-                                             uint32_t tD0, uint32_t tD1, uint32_t idesc, bool first) {
+                                             uint32_t tacc, int NT, int R, uint32_t idesc, int kb) {
   const uint64_t ah = smem_desc_sw128(a_addr), bh = smem_desc_sw128(b_addr);
   const uint64_t al = smem_desc_sw128(a_addr + a_plane), bl = smem_desc_sw128(b_addr + b_plane);
+  const uint32_t tD1 = tacc + (uint32_t)(R * NT);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const uint32_t acc = (first && k == 0) ? 0u : 1u;
-    mma_bf16_ss(tD0, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, acc);
+    const int ks = kb * 4 + k;
+    const int r = R == 1 ? 0 : ks % R;
+    mma_bf16_ss(tacc + (uint32_t)(r * NT), ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, ks >= R ? 1u : 0u);
     if (NS == 2) {
-      mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, acc);
+      mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, ks > 0 ? 1u : 0u);
       mma_bf16_ss(tD1, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
     }
   }
 }
 
 // ------------------------------------------------------------------------------ epilogue
+// 16 accumulator columns of this thread's row: sum of the R hi*hi accumulators (+ D1 * 2^-11)
+template <int NS>
+__device__ __forceinline__ void read_acc16(uint32_t tacc, int NT, int R, int c0, float (&o)[16]) {
+  uint32_t d[16];
+  tmem_ld16(tacc + (uint32_t)c0, d);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(d[j]);
+  for (int r = 1; r < R; ++r) {
+    tmem_ld16(tacc + (uint32_t)(r * NT + c0), d);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(d[j]);
+  }
+  if (NS == 2) {
+    tmem_ld16(tacc + (uint32_t)(R * NT + c0), d);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(d[j]), LO_INV, o[j]);
+  }
+}
+
 // One thread = one output row (TMEM lane).  tacc: TMEM address of D0 incl. the lane base.
 template <int NS>
 __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row) {
@@ -104,19 +133,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int
   const int px = m % Wp, t = m / Wp, py = t % Hp, b = t / Hp;
   const bool inP = m < p.P;
   const bool valid = inP && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
+  const int R = p.acc_r;
   if (p.epi == SGTA_EPI_STEM) {
     // N = 32: out[c] = relu(bn_a(acc[c])) + relu(bn_b(acc[16+c])), c < 16   (dla.py:325-331)
-    uint32_t a0[16], a1[16], b0[16], b1[16];
-    tmem_ld16(tacc, a0);
-    tmem_ld16(tacc + 16, b0);
-    if (NS == 2) { tmem_ld16(tacc + NT, a1); tmem_ld16(tacc + NT + 16, b1); }
-    tmem_ld_wait();
+    float fa[16], fb[16];
+    read_acc16<NS>(tacc, NT, R, 0, fa);
+    read_acc16<NS>(tacc, NT, R, 16, fb);
     if (valid) {
       float o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float va = __uint_as_float(a0[j]), vb = __uint_as_float(b0[j]);
-        if (NS == 2) { va = fmaf(__uint_as_float(a1[j]), LO_INV, va); vb = fmaf(__uint_as_float(b1[j]), LO_INV, vb); }
+        float va = fa[j], vb = fb[j];
         va = fmaf(va, __ldg(p.scale + j), __ldg(p.shift + j));
         vb = fmaf(vb, __ldg(p.scale + 16 + j), __ldg(p.shift + 16 + j));
         o[j] = fmaxf(va, 0.f) + fmaxf(vb, 0.f);
@@ -130,19 +157,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int
     return;
   }
   for (int c0 = 0; c0 < NT; c0 += 16) {
-    uint32_t d0[16], d1[16];
     __syncwarp();                      // tcgen05.ld is warp-collective: reconverge after the stores
-    tmem_ld16(tacc + (uint32_t)c0, d0);
-    if (NS == 2) tmem_ld16(tacc + (uint32_t)(NT + c0), d1);
-    tmem_ld_wait();
     const int n = n0 + c0;
     float o[16];
+    read_acc16<NS>(tacc, NT, R, c0, o);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float v = __uint_as_float(d0[j]);
-      if (NS == 2) v = fmaf(__uint_as_float(d1[j]), LO_INV, v);
-      o[j] = fmaf(v, __ldg(p.scale + n + j), __ldg(p.shift + n + j));
-    }
+    for (int j = 0; j < 16; ++j) o[j] = fmaf(o[j], __ldg(p.scale + n + j), __ldg(p.shift + n + j));
     if (p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC) {
       if (!valid) continue;
       if (p.res.base) {
@@ -228,6 +248,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t acc_stride = (uint32_t)((p.acc_r + NS - 1) * NT);
   const int total = p.m_tiles * p.n_tiles;
   const int Wp = p.x.W + 2;
   const int nb = p.taps == 9 ? 3 : 1;
@@ -272,11 +293,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
       uint32_t ac = 0, bc = 0, it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int m0 = (t / p.n_tiles) * TM;
-        const uint32_t as = it & 1u;
-        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+        const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
+        const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
+        mbar_wait(&acc_empty[as], (ause & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tD0 = tmem + as * (uint32_t)(NS * NT), tD1 = tD0 + (uint32_t)NT;
-        bool first = true;
+        const uint32_t tacc = tmem + as * acc_stride;
+        int kbi = 0;
         for (int kc = 0; kc < p.KC; ++kc) {
           for (int band = 0; band < nb; ++band) {
             const long long s = (long long)p.x.guard + m0 + (p.taps == 9 ? (band - 1) * Wp - 1 : 0);
@@ -289,8 +311,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
               mbar_wait(&b_full[sb], (bc / p.SB) & 1u);
               tc_fence_after();
               issue_kblock<NS>(a_base + (off + (uint32_t)dx) * 128u, a_plane, smem_u32(sB + (size_t)sb * b_stage),
-                               b_plane, tD0, tD1, idesc, first);
-              first = false;
+                               b_plane, tacc, NT, p.acc_r, idesc, kbi++);
               mma_commit(&b_empty[sb]);
               ++bc;
             }
@@ -307,10 +328,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      const uint32_t as = it & 1u;
-      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
+      const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
+      mbar_wait(&acc_full[as], ause & 1u);
       tc_fence_after();
-      epilogue_tile<NS>(p, tmem + as * (uint32_t)(NS * NT) + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+      epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -345,6 +367,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t acc_stride = (uint32_t)((p.acc_r + NS - 1) * NT);
   const int total = p.m_tiles * p.n_tiles;
   const int nkb = p.nkb;
 
@@ -519,16 +542,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
       const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
       uint32_t kc_cnt = 0, it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const uint32_t as = it & 1u;
-        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+        const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
+        const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
+        mbar_wait(&acc_empty[as], (ause & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tD0 = tmem + as * (uint32_t)(NS * NT), tD1 = tD0 + (uint32_t)NT;
+        const uint32_t tacc = tmem + as * acc_stride;
         for (int kb = 0; kb < nkb; ++kb, ++kc_cnt) {
           const uint32_t s = kc_cnt % (uint32_t)p.SA;
           mbar_wait(&full[s], (kc_cnt / (uint32_t)p.SA) & 1u);
           tc_fence_after();
           const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes);
-          issue_kblock<NS>(a0, a_plane, a0 + a_bytes, b_plane, tD0, tD1, idesc, kb == 0);
+          issue_kblock<NS>(a0, a_plane, a0 + a_bytes, b_plane, tacc, NT, p.acc_r, idesc, kb);
           mma_commit(&empty[s]);
         }
         mma_commit(&acc_full[as]);
@@ -540,10 +564,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      const uint32_t as = it & 1u;
-      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
+      const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
+      mbar_wait(&acc_full[as], ause & 1u);
       tc_fence_after();
-      epilogue_tile<NS>(p, tmem + as * (uint32_t)(NS * NT) + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+      epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -588,10 +613,14 @@ static int pick_ntile(int Cout, int NS) {
   }
   return nt;
 }
-static int tmem_cols_for(int NT, int NS) {
-  int need = 2 * NS * NT, c = 32;
+// accumulator plan: R hi*hi accumulators (+ D1) per stage; two stages when they fit in 512 columns
+static void plan_acc(ConvP& p, int NS) {
+  p.acc_r = NS == 2 ? 3 : 1;
+  const int per_stage = (p.acc_r + NS - 1) * p.NT;
+  p.acc_stages = 2 * per_stage <= 512 ? 2 : 1;
+  int need = p.acc_stages * per_stage, c = 32;
   while (c < need) c <<= 1;
-  return c;
+  p.tmem_cols = c;
 }
 
 template <int NS>
@@ -698,7 +727,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
   ConvP p{};
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
-  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; p.tmem_cols = tmem_cols_for(NT, NS);
+  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
   const int pad = ksize / 2;
   const int Ho = (x->H + 2 * pad - ksize) / stride + 1, Wo = (x->W + 2 * pad - ksize) / stride + 1;
   SGTA_REQUIRE(Ho > 0 && Wo > 0, "sgta_planes_conv: empty output");
@@ -748,7 +777,7 @@ extern "C" int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, cons
   ConvP p{};
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
-  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; p.tmem_cols = tmem_cols_for(NT, NS);
+  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
   const long long P = (long long)x->B * (Ho + 2) * (Wo + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv_sc: too many pixels");
   p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.m_tiles = cdiv(P, TM);
@@ -774,7 +803,7 @@ extern "C" int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, co
   p.om = (const float*)offset_mask;
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
   p.act = relu ? SGTA_ACT_RELU : SGTA_ACT_NONE; p.stride = 1; p.NT = NT; p.n_tiles = Cout / NT;
-  p.tmem_cols = tmem_cols_for(NT, NS);
+  plan_acc(p, NS);
   const long long P = (long long)x->B * (x->H + 2) * (x->W + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_dcn: too many pixels");
   p.P = (int)P; p.Ho = x->H; p.Wo = x->W; p.m_tiles = cdiv(P, TM);

@@ -24,7 +24,8 @@ mode="bf16": bf16 activations and MMAs, fp32 accumulate (stated looser bound, DE
 import torch
 import torch.nn.functional as F
 
-from . import _lib, decode, fastops as fo, fusion
+from . import decode, fusion
+from . import planes as P
 
 SCALE_LIST = (4, 2, 1, 1 / 2, 1 / 4, 1 / 8)
 BN_EPS = 1e-5
@@ -49,8 +50,7 @@ class InferenceEngine:
             raise ValueError("input size must be a multiple of 32")
         self.dev = torch.device(device)
         self.B, self.S, self.mode = batch, size, mode
-        self.mma = fo.MMA_F32X3 if mode == "fp32" else fo.MMA_BF16
-        self.adt = torch.float32 if mode == "fp32" else torch.bfloat16
+        self.ns = 2 if mode == "fp32" else 1
         self.opt = opt
         self.fuse_sigmoid = fuse_sigmoid
         self.skip_dead_levels = skip_dead_levels
@@ -62,55 +62,65 @@ class InferenceEngine:
         self._alloc()
         self.graph = None
         self._use_graph = use_graph
-        self._warm = False
 
     # ------------------------------------------------------------------ weights
-    def _conv_bn(self, pc, pb, stride, pad, act):
+    def _conv_bn(self, pc, pb, stride, act):
         w = self.sd[pc + ".weight"].float()
-        Cout, Cin, kh, kw = w.shape
+        Cout, Cin, k, _ = w.shape
         scale, shift = _fold_bn(self.sd, pb)
-        return fo.ConvSpec(fo.weight_matrix(w), scale, shift, Cin, kh, kw, stride, pad, self.mma, act)
+        return P.ConvSpec(P.weight_matrix(w), scale, shift, Cin, k, stride, self.ns, act)
+
+    def _sc_conv_bn(self, pc, pb, stride, in_W, act, pad=None):
+        w = self.sd[pc + ".weight"].float()
+        Cout, Cin, k, _ = w.shape
+        scale, shift = _fold_bn(self.sd, pb)
+        return P.ScConvSpec([(w, 0)], scale, shift, Cin, k, stride, k // 2 if pad is None else pad, 1, in_W,
+                            self.ns, act)
 
     def _block(self, p, stride):
-        return {"c1": self._conv_bn(p + ".conv1", p + ".bn1", stride, 1, fo.ACT_RELU),
-                "c2": self._conv_bn(p + ".conv2", p + ".bn2", 1, 1, fo.ACT_RELU)}   # relu after +residual
+        return {"c1": self._conv_bn(p + ".conv1", p + ".bn1", stride, P.ACT_RELU),
+                "c2": self._conv_bn(p + ".conv2", p + ".bn2", 1, P.ACT_RELU)}    # relu after +residual
 
     def _deform(self, p):
         sd = self.sd
         w = sd[p + ".conv.weight"].float()
         Cout, Cin = w.shape[:2]
         omw, omb = sd[p + ".conv.conv_offset_mask.weight"].float(), sd[p + ".conv.conv_offset_mask.bias"].float()
-        om = fo.ConvSpec(fo.weight_matrix(omw), torch.ones(27, device=self.dev), omb, Cin, 3, 3, 1, 1, self.mma,
-                         fo.ACT_NONE)                                # N padded 27 -> 32
+        om = P.ConvSpec(P.weight_matrix(omw), torch.ones(27, device=self.dev), omb, Cin, 3, 1, self.ns)  # N 27 -> 32
         scale, shift = _fold_bn(sd, p + ".actf.0", sd[p + ".conv.bias"])
-        return {"om": om, "w": fo.pack_dcn_weight(w, self.mma), "scale": scale.contiguous(),
-                "shift": shift.contiguous(), "Cin": Cin, "Cout": Cout}
+        return {"om": om, "w": P.ConvSpec(P.weight_matrix(w), scale, shift, Cin, 3, 1, self.ns, P.ACT_RELU),
+                "Cin": Cin, "Cout": Cout}
 
     def _build_specs(self):
-        sd, mma = self.sd, self.mma
+        sd, S = self.sd, self.S
         s = {}
-        # stem: one GEMM over [img(3) | hm(1)] channels, N = 16 (image conv) + 16 (heat-map conv)
+        # stem: ONE GEMM over [img(3) | hm(1)] channels, N = 16 (image conv) + 16 (heat-map conv)
         wi, wh = sd["base.pre_img_layer.0.weight"].float(), sd["base.pre_hm_layer.0.weight"].float()
-        wm = torch.cat([fo.weight_matrix(wi, 4, 0), fo.weight_matrix(wh, 4, 3)], 0)
         sa, ta = _fold_bn(sd, "base.pre_img_layer.1")
         sb, tb = _fold_bn(sd, "base.pre_hm_layer.1")
-        s["stem"] = fo.ConvSpec(wm, torch.cat([sa, sb]), torch.cat([ta, tb]), 4, 7, 7, 1, 3, mma)
-        s["level0"] = self._conv_bn("base.level0.0", "base.level0.1", 1, 1, fo.ACT_RELU)
-        s["level1"] = self._conv_bn("base.level1.0", "base.level1.1", 2, 1, fo.ACT_RELU)
+        s["stem"] = P.ScConvSpec([(wi, 0), (wh, 3)], torch.cat([sa, sb]), torch.cat([ta, tb]), 4, 7, 1, 3, 3, S,
+                                 self.ns)
+        s["level0"] = self._sc_conv_bn("base.level0.0", "base.level0.1", 1, S, P.ACT_RELU)
+        s["level1"] = self._sc_conv_bn("base.level1.0", "base.level1.1", 2, S, P.ACT_RELU)
+        # level2 = Tree(1, 32 -> 64, stride 2): its entry convolutions read SC maps
+        l2 = {"c1": self._sc_conv_bn("base.level2.tree1.conv1", "base.level2.tree1.bn1", 2, S // 2, P.ACT_RELU),
+              "c2": self._conv_bn("base.level2.tree1.conv2", "base.level2.tree1.bn2", 1, P.ACT_RELU)}
+        s["level2"] = {"tree1": l2, "tree2": self._block("base.level2.tree2", 1),
+                       "root": self._conv_bn("base.level2.root.conv", "base.level2.root.bn", 1, P.ACT_RELU),
+                       "project": self._sc_conv_bn("base.level2.project.0", "base.level2.project.1", 1, S // 4,
+                                                   P.ACT_NONE, pad=0)}
 
         def tree1(p, stride, project):
             t = {"tree1": self._block(p + ".tree1", stride), "tree2": self._block(p + ".tree2", 1),
-                 "root": self._conv_bn(p + ".root.conv", p + ".root.bn", 1, 0, fo.ACT_RELU)}
+                 "root": self._conv_bn(p + ".root.conv", p + ".root.bn", 1, P.ACT_RELU)}
             if project:
-                t["project"] = self._conv_bn(p + ".project.0", p + ".project.1", 1, 0, fo.ACT_NONE)
+                t["project"] = self._conv_bn(p + ".project.0", p + ".project.1", 1, P.ACT_NONE)
             return t
 
-        s["level2"] = tree1("base.level2", 2, True)
         for lv in (3, 4):
             p = "base.level%d" % lv
             s["level%d" % lv] = {"tree1": tree1(p + ".tree1", 2, True), "tree2": tree1(p + ".tree2", 1, False)}
         s["level5"] = tree1("base.level5", 2, True)
-        # DLAUp / IDAUp
         for name, n_nodes in (("dla_up.ida_0", 1), ("dla_up.ida_1", 2), ("dla_up.ida_2", 3), ("ida_up", 2)):
             for k in range(1, n_nodes + 1):
                 s["%s.proj_%d" % (name, k)] = self._deform("%s.proj_%d" % (name, k))
@@ -118,55 +128,53 @@ class InferenceEngine:
                 s["%s.up_%d" % (name, k)] = sd["%s.up_%d.weight" % (name, k)].float().contiguous()
         # heads: 64 -> 3 x 256 in one GEMM, then three 1x1 convs writing NCHW fp32
         self.head_names = [h for h in ("hm", "reg", "tracking") if (h + ".0.weight") in sd]
-        w0 = torch.cat([fo.weight_matrix(sd[h + ".0.weight"].float()) for h in self.head_names], 0)
+        w0 = torch.cat([P.weight_matrix(sd[h + ".0.weight"].float()) for h in self.head_names], 0)
         b0 = torch.cat([sd[h + ".0.bias"].float() for h in self.head_names])
-        s["head0"] = fo.ConvSpec(w0, torch.ones_like(b0), b0, 64, 3, 3, 1, 1, mma, fo.ACT_RELU)
+        s["head0"] = P.ConvSpec(w0, torch.ones_like(b0), b0, 64, 3, 1, self.ns, P.ACT_RELU)
         for h in self.head_names:
             w2, b2 = sd[h + ".2.weight"].float(), sd[h + ".2.bias"].float()
-            act = fo.ACT_SIGMOID if (h == "hm" and self.fuse_sigmoid) else fo.ACT_NONE
-            s["head2." + h] = fo.ConvSpec(fo.weight_matrix(w2), torch.ones_like(b2), b2, 256, 1, 1, 1, 0, mma,
-                                          act, n_valid=w2.shape[0])
+            act = P.ACT_SIGMOID if (h == "hm" and self.fuse_sigmoid) else P.ACT_NONE
+            s["head2." + h] = P.ConvSpec(P.weight_matrix(w2), torch.ones_like(b2), b2, 256, 1, 1, self.ns, act,
+                                         n_valid=w2.shape[0])
         self.specs = s
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
-        B, S, dev, adt = self.B, self.S, self.dev, self.adt
+        B, S, dev, ns = self.B, self.S, self.dev, self.ns
         B2 = 2 * B
-        z = lambda *shape, dtype=adt: torch.zeros(*shape, device=dev, dtype=dtype)
+        pb = lambda n, c, h, **kw: P.PlaneBuf(n, c, h, h, ns, dev, **kw)
+        h1, h2, h3, h4, h5 = S // 2, S // 4, S // 8, S // 16, S // 32
         b = {}
-        b["in4"] = z(B2, S, S, 4)
-        b["f0"] = z(B2, S, S, 16)
-        b["l0"] = z(B2, S, S, 16)
-        b["l1"] = z(B2, S // 2, S // 2, 32)
-        h2, h3, h4, h5 = S // 4, S // 8, S // 16, S // 32
-        b["bot2"] = z(B2, h2, h2, 32)
-        b["res2"] = z(B2, h2, h2, 64)
-        b["mid2"] = z(B2, h2, h2, 64)
-        b["cat2"] = z(B2, h2, h2, 128)
-        b["l2"] = z(B2, h2, h2, 64)
+        b["in4"] = pb(B2, 4, S, border=3)
+        b["f0"] = pb(B2, 16, S)
+        b["l0"] = pb(B2, 16, S)
+        b["l1"] = pb(B2, 32, h1)
+        b["bot2"] = pb(B2, 32, h2)
+        b["res2"] = pb(B2, 64, h2)
+        b["mid2"] = pb(B2, 64, h2)
+        b["cat2"] = pb(B2, 128, h2)
+        b["l2"] = pb(B2, 64, h2)
         for lv, c, h in ((3, 128, h3), (4, 256, h4)):
-            b["res%da" % lv] = z(B2, h, h, c)
-            b["mid%d" % lv] = z(B2, h, h, c)
-            b["cat%da" % lv] = z(B2, h, h, 2 * c)
-            b["cat%db" % lv] = z(B2, h, h, 3 * c + c // 2)
-            b["l%d" % lv] = z(B2, h, h, c)
-        b["res5"] = z(B2, h5, h5, 512)
-        b["mid5"] = z(B2, h5, h5, 512)
-        b["cat5"] = z(B2, h5, h5, 1280)
-        b["l5"] = z(B2, h5, h5, 512)
-        for i, (c, h) in enumerate(((16, S), (32, S // 2), (64, h2), (128, h3), (256, h4), (512, h5))):
-            b["fused%d" % i] = z(B, h, h, c)
-        b["om"] = z(B, h2, h2, 32, dtype=torch.float32)          # largest DCN map; reused by all 16
-        # DLAUp / IDAUp intermediates: proj output (at source res), sum (after up + skip), node output
+            b["res%da" % lv] = pb(B2, c, h)
+            b["mid%d" % lv] = pb(B2, c, h)
+            b["cat%da" % lv] = pb(B2, 2 * c, h)
+            b["cat%db" % lv] = pb(B2, 3 * c + c // 2, h)
+            b["l%d" % lv] = pb(B2, c, h)
+        b["res5"] = pb(B2, 512, h5)
+        b["mid5"] = pb(B2, 512, h5)
+        b["cat5"] = pb(B2, 1280, h5)
+        b["l5"] = pb(B2, 512, h5)
+
         def trio(name, c, hs, f):
-            b[name + ".p"] = z(B, hs, hs, c)
-            b[name + ".s"] = z(B, hs * f, hs * f, c)
-            b[name + ".n"] = z(B, hs * f, hs * f, c)
+            b[name + ".p"] = pb(B, c, hs)
+            b[name + ".s"] = pb(B, c, hs * f)
+            b[name + ".n"] = pb(B, c, hs * f)
         trio("dla_up.ida_0.1", 256, h5, 2)
         trio("dla_up.ida_1.1", 128, h4, 2); trio("dla_up.ida_1.2", 128, h4, 2)
         trio("dla_up.ida_2.1", 64, h3, 2); trio("dla_up.ida_2.2", 64, h3, 2); trio("dla_up.ida_2.3", 64, h3, 2)
         trio("ida_up.1", 64, h3, 2); trio("ida_up.2", 64, h4, 4)
-        b["hid"] = z(B, h2, h2, 256 * len(self.head_names))
+        b["hid"] = pb(B, 256 * len(self.head_names), h2)
+        self.om = torch.zeros(B * (h2 + 2) * (h2 + 2) + 256, 32, device=dev, dtype=torch.float32)
         self.out = {h: torch.zeros(B, self.specs["head2." + h].n_valid, h2, h2, device=dev, dtype=torch.float32)
                     for h in self.head_names}
         self.buf = b
@@ -176,52 +184,52 @@ class InferenceEngine:
                     "repro_hm_cls": torch.zeros(B, 7, h2, h2, device=dev)}
 
     # ------------------------------------------------------------------ plan pieces
-    def _basic_block(self, blk, x, ldx, xo, B, H, W, mid, res, ldres, reso, y, ldy, yo):
-        c1, c2 = blk["c1"], blk["c2"]
-        Ho, Wo = c1.out_hw(H, W)
-        fo.conv_nhwc(c1, x, B, H, W, ldx, mid, c1.Cout, x_coff=xo)
-        fo.conv_nhwc(c2, mid, B, Ho, Wo, c1.Cout, y, ldy, y_coff=yo, res=res, ldres=ldres, res_coff=reso)
-
-    def _tree1(self, t, x, ldx, xo, B, H, W, stride, cin, cout, bot, ldbot, boto, resbuf, mid, cat, ldcat,
-               out, ldout, outo):
-        """Tree(levels=1): children already sit in `cat` beyond [0, 2*cout).  `bot` is the
-        (pooled) input used for the projection / identity residual."""
-        Ho, Wo = H // stride, W // stride
+    def _tree1(self, t, x, bot, resbuf, mid, cat, cout, out):
+        """Tree(levels=1) (dla.py:178-231).  x: input view of tree1.conv1; bot: (pooled) input view
+        used for the projection / identity residual; cat: Root concat buffer whose channels
+        [0, 2*cout) receive [x2 | x1] (further children already sit behind them)."""
+        c1 = t["tree1"]["c1"]
         if "project" in t:
-            fo.conv_nhwc(t["project"], bot, B, Ho, Wo, ldbot, resbuf, cout, x_coff=boto)
-            res, ldres, reso = resbuf, cout, 0
+            if isinstance(t["project"], P.ScConvSpec):
+                P.conv_sc(t["project"], bot, resbuf.full, P.EPI_PL)
+            else:
+                P.conv(t["project"], bot, resbuf.full)
+            res = resbuf.full
         else:
-            res, ldres, reso = bot, ldbot, boto
-        # x1 -> cat[:, cout:2cout], x2 -> cat[:, 0:cout]
-        self._basic_block(t["tree1"], x, ldx, xo, B, H, W, mid, res, ldres, reso, cat, ldcat, cout)
-        self._basic_block(t["tree2"], cat, ldcat, cout, B, Ho, Wo, mid, cat, ldcat, cout, cat, ldcat, 0)
-        fo.conv_nhwc(t["root"], cat, B, Ho, Wo, ldcat, out, ldout, y_coff=outo)
+            res = bot
+        x1, x2 = cat.view(c0=cout, C=cout), cat.view(c0=0, C=cout)
+        if isinstance(c1, P.ScConvSpec):
+            P.conv_sc(c1, x, mid.full, P.EPI_PL)
+        else:
+            P.conv(c1, x, mid.full)
+        P.conv(t["tree1"]["c2"], mid.full, x1, res=res)
+        P.conv(t["tree2"]["c1"], x1, mid.full)
+        P.conv(t["tree2"]["c2"], mid.full, x2, res=x1)
+        P.conv(t["root"], cat.full, out)
 
-    def _deform_conv(self, d, x, B, H, W, y):
-        om = self.buf["om"]
-        fo.conv_nhwc(d["om"], x, B, H, W, d["Cin"], om, 32)
-        _lib.call("sgta_dcn_forward_nhwc", _lib.ptr(x), _lib.ptr(om), _lib.ptr(d["w"]), _lib.ptr(d["scale"]),
-                  _lib.ptr(d["shift"]), _lib.ptr(y), B, d["Cin"], d["Cout"], H, W, self.mma, 1,
-                  fo._dt(y.dtype), _lib.stream())
+    def _deform_conv(self, d, x, y):
+        P.conv(d["om"], x, y_f32=self.om, ld_f32=32, epi=P.EPI_F32ROWS)
+        P.dcn(x, self.om, d["w"], d["w"].scale, d["w"].shift, y, relu=True)
 
-    def _ida_step(self, name, k, src, hs, skip, f):
+    def _ida_step(self, name, k, src, skip, f):
         """layers[i] = node(up(proj(layers[i])) + layers[i-1])   (dla.py:571-577)"""
-        s, b, B = self.specs, self.buf, self.B
+        s, b = self.specs, self.buf
         key = "%s.%d" % (name, k)
         proj, node = s["%s.proj_%d" % (name, k)], s["%s.node_%d" % (name, k)]
-        self._deform_conv(proj, src, B, hs, hs, b[key + ".p"])
-        c = proj["Cout"]
-        fo.upsample_add(b[key + ".p"], s["%s.up_%d" % (name, k)], skip, c, b[key + ".s"], c, B, hs, hs, c, f)
-        self._deform_conv(node, b[key + ".s"], B, hs * f, hs * f, b[key + ".n"])
-        return b[key + ".n"]
+        self._deform_conv(proj, src, b[key + ".p"].full)
+        P.upsample_add(b[key + ".p"].full, s["%s.up_%d" % (name, k)], skip, b[key + ".s"].full, proj["Cout"], f)
+        self._deform_conv(node, b[key + ".s"].full, b[key + ".n"].full)
+        return b[key + ".n"].full
 
     def _fuse_level(self, i, feats, pre_flat, rep_flat, Whm):
+        """Structure-prior fusion of level i, written back IN PLACE into the current-frame half of
+        `feats` (dla.py:1513-1546)."""
         B, sd = self.B, self.sd
-        _, H, W, C = feats.shape
+        C, H, W = feats.C, feats.H, feats.W
         pre_ids = fusion.window_ids(pre_flat[i], Whm, SCALE_LIST[i], self.kernel_list[i], H, W)
         cur_ids = fusion.window_ids(rep_flat[i], Whm, SCALE_LIST[i], self.kernel_list[i], H, W)
-        pre_key = fo.gather_tokens_nhwc(feats[:B], C, pre_ids, C, H * W)
-        cur_q = fo.gather_tokens_nhwc(feats[B:], C, cur_ids, C, H * W)
+        pre_key = P.gather_tokens(feats.full, 0, pre_ids, C)
+        cur_q = P.gather_tokens(feats.full, B, cur_ids, C)
         out = pre_key
         if i <= 2:
             p = "transformer.%d.layers.0" % i
@@ -243,45 +251,38 @@ class InferenceEngine:
         c = "cat_layer.%d" % i
         rows = F.linear(F.relu(F.linear(torch.cat([out, cur_q], -1), sd[c + ".0.weight"], sd[c + ".0.bias"])),
                         sd[c + ".2.weight"], sd[c + ".2.bias"])
-        fused = self.buf["fused%d" % i]
-        fused.copy_(feats[B:])
-        fo.scatter_tokens_nhwc(fused, C, cur_ids, rows, C, H * W)
-        return fused
+        P.scatter_tokens(feats.full, B, cur_ids, rows, C)
+        return feats.view(B, B)
 
     # ------------------------------------------------------------------ the plan
     def _run(self):
-        s, b, B, S = self.specs, self.buf, self.B, self.S
-        B2 = 2 * B
+        s, b, B = self.specs, self.buf, self.B
         i = self.inp
-        in4 = b["in4"]
-        fo.nchw_to_nhwc(i["pre_img"], in4[:B], 4, 0)
-        fo.nchw_to_nhwc(i["pre_hm"], in4[:B], 4, 3)
-        fo.nchw_to_nhwc(i["x"], in4[B:], 4, 0)
-        fo.nchw_to_nhwc(i["repro_hm"], in4[B:], 4, 3)
-        fo.conv_nhwc(s["stem"], in4, B2, S, S, 4, b["f0"], 16, epi=fo.EPI_STEM)
-        fo.conv_nhwc(s["level0"], b["f0"], B2, S, S, 16, b["l0"], 16)
-        fo.conv_nhwc(s["level1"], b["l0"], B2, S, S, 16, b["l1"], 32)
-        h1, h2, h3, h4, h5 = S // 2, S // 4, S // 8, S // 16, S // 32
+        P.pack_stem(i["pre_img"], i["pre_hm"], b["in4"].full, 0)
+        P.pack_stem(i["x"], i["repro_hm"], b["in4"].full, B)
+        P.conv_sc(s["stem"], b["in4"].full, b["f0"].full, P.EPI_STEM)
+        P.conv_sc(s["level0"], b["f0"].full, b["l0"].full, P.EPI_SC)
+        P.conv_sc(s["level1"], b["l0"].full, b["l1"].full, P.EPI_SC)
         # level 2: Tree(1, 32->64, stride 2)
-        fo.maxpool2(b["l1"], B2, h1, h1, 32, 32, b["bot2"], 32)
-        self._tree1(s["level2"], b["l1"], 32, 0, B2, h1, h1, 2, 32, 64, b["bot2"], 32, 0, b["res2"], b["mid2"],
-                    b["cat2"], 128, b["l2"], 64, 0)
+        P.maxpool2(b["l1"].full, b["bot2"].full, 32)
+        self._tree1(s["level2"], b["l1"].full, b["bot2"].full, b["res2"], b["mid2"], b["cat2"], 64, b["l2"].full)
         # levels 3, 4: Tree(2, c/2 -> c, stride 2, level_root): cat_b = [x2 | x1 | bottom | tree1 out]
-        prev, hp, cp = b["l2"], h2, 64
-        for lv, c, h in ((3, 128, h3), (4, 256, h4)):
+        prev, cp = b["l2"], 64
+        for lv, c in ((3, 128), (4, 256)):
             t = s["level%d" % lv]
-            catb, ldb = b["cat%db" % lv], 3 * c + c // 2
-            fo.maxpool2(prev, B2, hp, hp, cp, cp, catb, ldb, y_coff=2 * c)                # bottom -> children
-            self._tree1(t["tree1"], prev, cp, 0, B2, hp, hp, 2, cp, c, catb, ldb, 2 * c, b["res%da" % lv],
-                        b["mid%d" % lv], b["cat%da" % lv], 2 * c, catb, ldb, 2 * c + cp)     # x1 -> children
-            self._tree1(t["tree2"], catb, ldb, 2 * c + cp, B2, h, h, 1, c, c, catb, ldb, 2 * c + cp, None,
-                        b["mid%d" % lv], catb, ldb, b["l%d" % lv], c, 0)
-            prev, hp, cp = b["l%d" % lv], h, c
+            catb = b["cat%db" % lv]
+            bottom = catb.view(c0=2 * c, C=cp)
+            P.maxpool2(prev.full, catb.full, cp, 0, 2 * c)                         # bottom -> children
+            x1o = catb.view(c0=2 * c + cp, C=c)
+            self._tree1(t["tree1"], prev.full, bottom, b["res%da" % lv], b["mid%d" % lv], b["cat%da" % lv], c, x1o)
+            self._tree1(t["tree2"], x1o, x1o, None, b["mid%d" % lv], catb, c, b["l%d" % lv].full)
+            prev, cp = b["l%d" % lv], c
         # level 5: Tree(1, 256->512, stride 2, level_root): cat = [x2 | x1 | bottom]
-        fo.maxpool2(b["l4"], B2, h4, h4, 256, 256, b["cat5"], 1280, y_coff=1024)
-        self._tree1(s["level5"], b["l4"], 256, 0, B2, h4, h4, 2, 256, 512, b["cat5"], 1280, 1024, b["res5"],
-                    b["mid5"], b["cat5"], 1280, b["l5"], 512, 0)
+        P.maxpool2(b["l4"].full, b["cat5"].full, 256, 0, 1024)
+        self._tree1(s["level5"], b["l4"].full, b["cat5"].view(c0=1024, C=256), b["res5"], b["mid5"], b["cat5"], 512,
+                    b["l5"].full)
         # structure-prior fusion
+        Whm = i["pre_hm_cls"].shape[3]
         pre_flat, rep_flat = {}, {}
         for K in set(self.K_list):
             p, r = fusion.topk_flat_index(i["pre_hm_cls"], K), fusion.topk_flat_index(i["repro_hm_cls"], K)
@@ -292,24 +293,27 @@ class InferenceEngine:
         for lv in range(6):
             if lv < 2 and self.skip_dead_levels:
                 continue                     # levels 0/1 never reach the output (DLAUp starts at level 2)
-            fused[lv] = self._fuse_level(lv, b["l%d" % lv], pre_flat, rep_flat, h2)
+            fused[lv] = self._fuse_level(lv, b["l%d" % lv], pre_flat, rep_flat, Whm)
         # DLAUp (dla.py:600-606)
-        a5 = self._ida_step("dla_up.ida_0", 1, fused[5], h5, fused[4], 2)                  # 256 @ h4
-        b4 = self._ida_step("dla_up.ida_1", 1, fused[4], h4, fused[3], 2)                  # 128 @ h3
-        b5 = self._ida_step("dla_up.ida_1", 2, a5, h4, b4, 2)
-        c3 = self._ida_step("dla_up.ida_2", 1, fused[3], h3, fused[2], 2)                  # 64 @ h2
-        c4 = self._ida_step("dla_up.ida_2", 2, b4, h3, c3, 2)
-        c5 = self._ida_step("dla_up.ida_2", 3, b5, h3, c4, 2)
+        a5 = self._ida_step("dla_up.ida_0", 1, fused[5], fused[4], 2)                  # 256 @ h4
+        b4 = self._ida_step("dla_up.ida_1", 1, fused[4], fused[3], 2)                  # 128 @ h3
+        b5 = self._ida_step("dla_up.ida_1", 2, a5, b4, 2)
+        c3 = self._ida_step("dla_up.ida_2", 1, fused[3], fused[2], 2)                  # 64 @ h2
+        c4 = self._ida_step("dla_up.ida_2", 2, b4, c3, 2)
+        c5 = self._ida_step("dla_up.ida_2", 3, b5, c4, 2)
         # IDAUp over [c5 (64@h2), b5 (128@h3), a5 (256@h4)]  (dla.py:1548-1552)
-        y1 = self._ida_step("ida_up", 1, b5, h3, c5, 2)
-        y2 = self._ida_step("ida_up", 2, a5, h4, y1, 4)
+        y1 = self._ida_step("ida_up", 1, b5, c5, 2)
+        y2 = self._ida_step("ida_up", 2, a5, y1, 4)
         # heads
-        nh = len(self.head_names)
-        fo.conv_nhwc(s["head0"], y2, B, h2, h2, 64, b["hid"], 256 * nh)
+        P.conv(s["head0"], y2, b["hid"].full)
         for j, h in enumerate(self.head_names):
-            fo.conv_nhwc(s["head2." + h], b["hid"], B, h2, h2, 256 * nh, self.out[h], 0, x_coff=256 * j,
-                         epi=fo.EPI_NCHW)
-        self.feat = y2
+            P.conv(s["head2." + h], b["hid"].view(c0=256 * j, C=256), y_f32=self.out[h], epi=P.EPI_NCHW)
+        self.feat_view = y2
+
+    @property
+    def feat(self):
+        """[B,64,H/4,W/4] fp32 NCHW copy of the feature map the heads read (y[-1], dla.py:1552)."""
+        return self.feat_view.to_nchw()
 
     # ------------------------------------------------------------------ public API
     def forward(self, x, pre_img, pre_hm, repro_hm, pre_hm_cls, repro_hm_cls):

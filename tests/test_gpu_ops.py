@@ -405,7 +405,7 @@ def test_engine_golden(golden, mode, graph):
     for rep in range(2):                       # second call exercises graph replay
         out = eng(*[t.to(DEV) for t in ins])[0]
     tol = 1e-3 if mode == "fp32" else 6e-2
-    feat = eng.feat.float().permute(0, 3, 1, 2).cpu()
+    feat = eng.feat.cpu()
     assert rel_err(feat, torch.from_numpy(g["feat"])) < tol
     for k in ("hm", "reg", "tracking"):
         assert rel_err(out[k].cpu(), torch.from_numpy(g[k])) < tol, k

@@ -62,16 +62,24 @@ for mode in ("fp32", "bf16"):
     eo = eng(*ins)[0]
     torch.cuda.synchronize()
     print("==== mode", mode)
-    nchw = lambda t: t.float().permute(0, 3, 1, 2)
+    nchw = lambda t: t.to_nchw()
     f0 = cap["stem_img"][0] + cap["stem_hm"][0]
     f1 = cap["stem_img"][1] + cap["stem_hm"][1]
-    print("stem pre %.3e cur %.3e" % (rel(nchw(eng.buf["f0"][:B]), f0), rel(nchw(eng.buf["f0"][B:]), f1)))
+    ef0 = nchw(eng.buf["f0"])
+    print("stem pre %.3e cur %.3e" % (rel(ef0[:B], f0), rel(ef0[B:], f1)))
     for i in range(6):
         e = nchw(eng.buf["l%d" % i])
-        print("l%d pre %.3e cur %.3e" % (i, rel(e[:B], cap["l%d" % i][0]), rel(e[B:], cap["l%d" % i][1])))
+        print("l%d pre %.3e" % (i, rel(e[:B], cap["l%d" % i][0])))
     for i in range(6):
-        print("fused%d %.3e" % (i, rel(nchw(eng.buf["fused%d" % i]), cap["fused%d" % i][0])))
+        print("fused%d %.3e" % (i, rel(nchw(eng.buf["l%d" % i])[B:], cap["fused%d" % i][0])))
     for key in sorted(k for k in cap if k.endswith((".p", ".s", ".n"))):
         print("%s %.3e" % (key, rel(nchw(eng.buf[key]), cap[key][0])))
     for k in ("hm", "reg", "tracking"):
         print(k, "%.3e" % rel(eo[k], out[k]))
+    if S == 128:
+        import numpy as np
+        g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "model_S128.npz"))
+        for k in ("hm", "reg", "tracking"):
+            gk = torch.from_numpy(g[k]).to(DEV)
+            print(k, "engine vs golden %.3e   eager vs golden %.3e" % (rel(eo[k], gk), rel(out[k], gk)))
+        print("feat engine vs golden %.3e" % rel(eng.feat, torch.from_numpy(g["feat"]).to(DEV)))
