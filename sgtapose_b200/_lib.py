@@ -30,6 +30,7 @@ _V = _c.POINTER(SgtaPlanes)
 
 # name -> (restype, argtypes); mirrors include/sgta_b200.h one to one
 SIGNATURES = {
+    "sgta_debug_flags": (_I, [_I]),
     "sgta_planes_guard": (_I, [_I]),
     "sgta_planes_ntile": (_I, [_I, _I]),
     "sgta_planes_wpack_bytes": (_c.c_int64, [_I, _I, _I]),

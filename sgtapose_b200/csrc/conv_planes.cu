@@ -37,7 +37,9 @@ constexpr int TM = 128;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int G_PROD_WARPS = 8;
 constexpr int G_THREADS = (G_PROD_WARPS + 2 + 4) * 32;   // producers, B loader, MMA, 4 epilogue warps
-constexpr int S_THREADS = 6 * 32;                        // TMA, MMA, 4 epilogue warps
+constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
+                                                         // each, tests/cuda/tma_bw_probe.cu): spread them over 4
+constexpr int S_THREADS = (S_TMA_WARPS + 1 + 4) * 32;    // TMA warps, MMA, 4 epilogue warps
 
 enum { PROD_DCN = 0, PROD_STRIDE = 1, PROD_SMALLC = 2 };
 
@@ -63,7 +65,20 @@ struct ConvP {
   int seg_groups;        // SMALLC: 16-byte groups per segment (8 or 4)
   int seg_off[16];       // SMALLC: input row offset of segment j of K block kb at [kb*2 + j]
   int vec8;              // SMALLC: rows are only 8-byte aligned (C = 4)
+  unsigned long long magic_wp, magic_hp;   // ceil(2^64 / (Wo+2)), ceil(2^64 / (Ho+2)): exact m / d for m < 2^32
+  int dbg;               // tools/conv_bench.py: 1 = skip A copies, 2 = skip B copies, 4 = skip epilogue math
 };
+
+static int g_dbg = 0;
+
+// m -> (px, py, b) of the zero-bordered output frame, without integer division
+__device__ __forceinline__ void decode_row(const ConvP& p, int m, int& px, int& py, int& b) {
+  const uint32_t t = (uint32_t)__umul64hi((unsigned long long)(uint32_t)m, p.magic_wp);
+  px = m - (int)t * (p.Wo + 2);
+  b = (int)__umul64hi((unsigned long long)t, p.magic_hp);
+  py = (int)t - b * (p.Ho + 2);
+}
+static unsigned long long magic_u64(unsigned d) { return d <= 1 ? ~0ull : (~0ull / d) + 1; }
 
 __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -83,23 +98,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // each.  The tensor core TRUNCATES when it adds a K=16 dot product into the fp32 accumulator
 // (measured: -2.7e-5 relative on an all-positive K=4608 sum), so in the fp32-parity mode the hi*hi
 // products rotate over R accumulators that the epilogue adds in round-to-nearest fp32.
-template <int NS>
-__device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
-                                             uint32_t tacc, int NT, int R, uint32_t idesc, int kb) {
+template <int NS, bool FIRST, int R>
+__device__ __forceinline__ void issue_kblock_impl(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
+                                                  uint32_t tacc, uint32_t NT, uint32_t idesc, int rb) {
+  // everything but the 14-bit start-address field of a descriptor is constant: build the four
+  // descriptors once, then only add 2 (= 32 bytes >> 4) per K step -- the single issuing thread
+  // must stay well under one MMA duration (32 clk at N = 64) per instruction
   const uint64_t ah = smem_desc_sw128(a_addr), bh = smem_desc_sw128(b_addr);
   const uint64_t al = smem_desc_sw128(a_addr + a_plane), bl = smem_desc_sw128(b_addr + b_plane);
-  const uint32_t tD1 = tacc + (uint32_t)(R * NT);
+  const uint32_t tD1 = tacc + (uint32_t)R * NT;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int ks = kb * 4 + k;
-    const int r = R == 1 ? 0 : ks % R;
-    mma_bf16_ss(tacc + (uint32_t)(r * NT), ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, ks >= R ? 1u : 0u);
+    int r = 0;
+    if (R > 1) { r = rb + k; r = r >= R ? r - R : r; }
+    const uint32_t tD0 = tacc + (uint32_t)r * NT;
+    mma_bf16_ss(tD0, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, (FIRST && k < R) ? 0u : 1u);
     if (NS == 2) {
-      mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, ks > 0 ? 1u : 0u);
+      mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, (FIRST && k == 0) ? 0u : 1u);
       mma_bf16_ss(tD1, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
     }
   }
 }
+// rb = (first K step of this block) mod R, maintained incrementally by the caller
+template <int NS, int R>
+__device__ __forceinline__ void issue_kblock_r(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
+                                               uint32_t tacc, int NT, uint32_t idesc, bool first, int rb) {
+  if (first) issue_kblock_impl<NS, true, R>(a_addr, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0);
+  else issue_kblock_impl<NS, false, R>(a_addr, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb);
+}
+template <int NS>
+__device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
+                                             uint32_t tacc, int NT, int R, uint32_t idesc, bool first, int rb) {
+  switch (R) {
+    case 1: issue_kblock_r<NS, 1>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
+    case 2: issue_kblock_r<NS, 2>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
+    case 3: issue_kblock_r<NS, 3>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
+    default: issue_kblock_r<NS, 4>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
+  }
+}
+// 4 K steps per block: the rotation start advances by 4 mod R
+__device__ __forceinline__ int next_rb(int rb, int R) { return R == 3 ? (rb == 2 ? 0 : rb + 1) : 0; }
 
 // ------------------------------------------------------------------------------ epilogue
 // 16 accumulator columns of this thread's row: sum of the R hi*hi accumulators (+ D1 * 2^-11)
@@ -129,8 +167,8 @@ template <int NS>
 __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row) {
   const int NT = p.NT;
   const int m = m0 + row;
-  const int Wp = p.Wo + 2, Hp = p.Ho + 2;
-  const int px = m % Wp, t = m / Wp, py = t % Hp, b = t / Hp;
+  int px, py, b;
+  decode_row(p, m, px, py, b);
   const bool inP = m < p.P;
   const bool valid = inP && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
   const int R = p.acc_r;
@@ -239,11 +277,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], NS); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  if (warp == S_TMA_WARPS) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -254,93 +292,112 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   const int nb = p.taps == 9 ? 3 : 1;
   const int ntap_b = p.taps == 9 ? 3 : 1;
 
-  if (warp == 0) {
+  if (warp < S_TMA_WARPS) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      uint32_t ac = 0, bc = 0;
+      // ---------------------------------------------------------------- TMA producers
+      // every copy (one plane of an A band, one B tile) belongs to a FIXED warp per ring slot, so the
+      // rounds of a slot are issued in order by one thread (a parity wait two rounds early would pass)
+      // ring positions are tracked incrementally (a runtime % or / per K block costs ~100 clk on
+      // a single thread, more than the MMAs it feeds)
+      int st = 0, sb = 0;
+      uint32_t aph = 1, bph = 1;           // parity to wait for on the *_empty barriers
+      const bool skipA = p.dbg & 1, skipB = p.dbg & 2;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+        const unsigned char* wt = p.wpack + (size_t)nt * p.nkb * b_stage;
         for (int kc = 0; kc < p.KC; ++kc) {
           for (int band = 0; band < nb; ++band) {
             const long long s = (long long)p.x.guard + m0 + (p.taps == 9 ? (band - 1) * Wp - 1 : 0);
             const long long s8 = s & ~7ll;
-            const int st = ac % p.SA;
-            mbar_wait(&a_empty[st], ((ac / p.SA) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&a_full[st], a_stage);
 #pragma unroll
-            for (int pl = 0; pl < NS; ++pl)
+            for (int pl = 0; pl < NS; ++pl) {
+              if (((st * NS + pl) & (S_TMA_WARPS - 1)) != warp) continue;
+              mbar_wait(&a_empty[st], aph);
+              if (skipA) { mbar_arrive(&a_full[st]); continue; }
+              mbar_arrive_expect_tx(&a_full[st], a_plane);
               bulk_g2s(sA + (size_t)st * a_stage + pl * a_plane,
                        p.x.base + ((((size_t)pl * p.x.nchunks + p.x.chunk0 + kc) * p.x.rows + s8) << 7), a_plane,
                        &a_full[st]);
-            ++ac;
+            }
+            if (++st == p.SA) { st = 0; aph ^= 1u; }
             for (int dx = 0; dx < ntap_b; ++dx) {
-              const int tap = band * ntap_b + dx;
-              const int sb = bc % p.SB;
-              mbar_wait(&b_empty[sb], ((bc / p.SB) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&b_full[sb], b_stage);
-              bulk_g2s(sB + (size_t)sb * b_stage, p.wpack + ((size_t)nt * p.nkb + (size_t)tap * p.KC + kc) * b_stage,
-                       b_stage, &b_full[sb]);
-              ++bc;
+              if (((sb + 2) & (S_TMA_WARPS - 1)) == warp) {
+                mbar_wait(&b_empty[sb], bph);
+                if (skipB) mbar_arrive(&b_full[sb]);
+                else {
+                  const int tap = band * ntap_b + dx;
+                  mbar_arrive_expect_tx(&b_full[sb], b_stage);
+                  bulk_g2s(sB + (size_t)sb * b_stage, wt + ((size_t)tap * p.KC + kc) * b_stage, b_stage, &b_full[sb]);
+                }
+              }
+              if (++sb == p.SB) { sb = 0; bph ^= 1u; }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
-      uint32_t ac = 0, bc = 0, it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int m0 = (t / p.n_tiles) * TM;
-        const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
-        const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
-        mbar_wait(&acc_empty[as], (ause & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t tacc = tmem + as * acc_stride;
-        int kbi = 0;
-        for (int kc = 0; kc < p.KC; ++kc) {
-          for (int band = 0; band < nb; ++band) {
-            const long long s = (long long)p.x.guard + m0 + (p.taps == 9 ? (band - 1) * Wp - 1 : 0);
-            const uint32_t off = (uint32_t)(s & 7ll);
-            const int st = ac % p.SA;
-            mbar_wait(&a_full[st], (ac / p.SA) & 1u);
-            const uint32_t a_base = smem_u32(sA + (size_t)st * a_stage);
-            for (int dx = 0; dx < ntap_b; ++dx) {
-              const int sb = bc % p.SB;
-              mbar_wait(&b_full[sb], (bc / p.SB) & 1u);
-              tc_fence_after();
-              issue_kblock<NS>(a_base + (off + (uint32_t)dx) * 128u, a_plane, smem_u32(sB + (size_t)sb * b_stage),
-                               b_plane, tacc, NT, p.acc_r, idesc, kbi++);
+  } else if (warp == S_TMA_WARPS) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp
+    // walks the loop and waits; one elected lane issues, so operands stay in uniform registers)
+    const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+    int st = 0, sb = 0;
+    uint32_t aph = 0, bph = 0;             // parity to wait for on the *_full barriers
+    uint32_t as = 0, accph = 1;            // accumulator stage and parity of its acc_empty barrier
+    const uint32_t a_smem = smem_u32(sA), b_smem = smem_u32(sB);
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int m0 = (t / p.n_tiles) * TM;
+      mbar_wait(&acc_empty[as], accph);
+      tc_fence_after();
+      const uint32_t tacc = tmem + as * acc_stride;
+      int rb = 0;
+      bool first = true;
+      for (int kc = 0; kc < p.KC; ++kc) {
+        for (int band = 0; band < nb; ++band) {
+          const long long s = (long long)p.x.guard + m0 + (p.taps == 9 ? (band - 1) * Wp - 1 : 0);
+          const uint32_t off = (uint32_t)(s & 7ll);
+          if (!(p.dbg & 8)) mbar_wait(&a_full[st], aph);
+          const uint32_t a_base = a_smem + (uint32_t)st * a_stage + off * 128u;
+          for (int dx = 0; dx < ntap_b; ++dx) {
+            if (!(p.dbg & 8)) mbar_wait(&b_full[sb], bph);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_kblock<NS>(a_base + (uint32_t)dx * 128u, a_plane, b_smem + (uint32_t)sb * b_stage, b_plane, tacc, NT,
+                               p.acc_r, idesc, first, rb);
               mma_commit(&b_empty[sb]);
-              ++bc;
             }
-            mma_commit(&a_empty[st]);
-            ++ac;
+            rb = next_rb(rb, p.acc_r);
+            __syncwarp();
+            first = false;
+            if (++sb == p.SB) { sb = 0; bph ^= 1u; }
           }
+          if (elect_one()) mma_commit(&a_empty[st]);
+          __syncwarp();
+          if (++st == p.SA) { st = 0; aph ^= 1u; }
         }
-        mma_commit(&acc_full[as]);
       }
+      if (elect_one()) mma_commit(&acc_full[as]);
+      __syncwarp();
+      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    uint32_t as = 0, accph = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
-      const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
-      mbar_wait(&acc_full[as], ause & 1u);
+      mbar_wait(&acc_full[as], accph);
       tc_fence_after();
-      epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+      if (!(p.dbg & 4))
+        epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc_dyn(tmem, p.tmem_cols);
+  if (warp == S_TMA_WARPS) tmem_dealloc_dyn(tmem, p.tmem_cols);
 }
 
 // =============================================================================== gather kernel
@@ -355,6 +412,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.SA * stage_bytes);
   uint64_t *full = bars, *empty = bars + 8, *acc_full = bars + 16, *acc_empty = bars + 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 32);      // DCN sampling table (9*128*20 B)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -373,74 +431,82 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
 
   if (warp < G_PROD_WARPS) {
     // ================================================================== A producers
+    // lane = (sub, c8): 8 lanes cover one 128-byte row, a warp-wide load covers 4 whole rows
     const int sub = lane >> 3, c8 = lane & 7;
-    const int Wpo = p.Wo + 2, Hpo = p.Ho + 2;
     const int iWp = p.in_Wp, iHp = p.in_Hp;
-    uint32_t kc_cnt = 0;   // K blocks produced so far (ring position)
+    int pst = 0;           // ring slot and parity of its empty barrier
+    uint32_t pph = 1;
+    auto wait_stage = [&]() -> unsigned char* {
+      mbar_wait(&empty[pst], pph);
+      return smem + (size_t)pst * stage_bytes;
+    };
+    auto publish = [&]() {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[pst]);
+      if (++pst == p.SA) { pst = 0; pph ^= 1u; }
+    };
+    const size_t plane_bytes = ((size_t)p.x.nchunks * p.x.rows) << 7;     // PL inputs
+    uint32_t soff[4];      // swizzled byte offset of this thread's 16-byte group in each of its rows
+    int rr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rr[i] = warp * 16 + i * 4 + sub;
+      soff[i] = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
+    }
+
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int m0 = (t / p.n_tiles) * TM;
-      int rr[4];          // tile rows of this thread
-      int fb[4];          // input frame base row (b * iHp * iWp)
-      int oy[4], ox[4];   // clamped unpadded output coordinates
-      bool ok[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        rr[i] = warp * 16 + i * 4 + sub;
-        const int m = m0 + rr[i];
-        const int px = m % Wpo, tq = m / Wpo, py = tq % Hpo;
-        int b = tq / Hpo;
-        ok[i] = m < p.P && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
-        b = min(b, p.x.B - 1);
-        oy[i] = min(max(py - 1, 0), p.Ho - 1);
-        ox[i] = min(max(px - 1, 0), p.Wo - 1);
-        fb[i] = b * iHp * iWp;
-      }
-      auto wait_stage = [&](uint32_t kc) -> unsigned char* {
-        const uint32_t s = kc % (uint32_t)p.SA;
-        mbar_wait(&empty[s], ((kc / (uint32_t)p.SA) & 1u) ^ 1u);
-        return smem + (size_t)s * stage_bytes;
-      };
-      auto publish = [&](uint32_t kc) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[kc % (uint32_t)p.SA]);
-      };
-
       if (PROD == PROD_DCN) {
-        for (int tap = 0; tap < 9; ++tap) {
-          int q00[4];
-          float w00[4], w01[4], w10[4], w11[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float* om = p.om + (size_t)(m0 + rr[i]) * 32;
-            float dy = 0.f, dx = 0.f, ml = 0.f;
-            if (ok[i]) { dy = __ldg(om + 2 * tap); dx = __ldg(om + 2 * tap + 1); ml = __ldg(om + 18 + tap); }
-            // padded-frame coordinates: unpadded + 1
-            float sy = (float)(oy[i] + tap / 3) + dy;
-            float sx = (float)(ox[i] + tap % 3) + dx;
-            const bool in = ok[i] && sy > 0.f && sy < (float)(p.Ho + 1) && sx > 0.f && sx < (float)(p.Wo + 1);
-            float msk = in ? 1.f / (1.f + __expf(-ml)) : 0.f;
-            sy = in ? sy : 0.f;
-            sx = in ? sx : 0.f;
-            const float yf = floorf(sy), xf = floorf(sx);
-            const float ly = sy - yf, lx = sx - xf, hy = 1.f - ly, hx = 1.f - lx;
-            w00[i] = msk * hy * hx; w01[i] = msk * hy * lx; w10[i] = msk * ly * hx; w11[i] = msk * ly * lx;
-            q00[i] = fb[i] + (int)yf * iWp + (int)xf;
+        // ---- per tile: sampling table in shared memory (one entry per (tap, row)): corner-00 row
+        // index and the four mask*bilinear weights; every lane of a row reads it back (broadcast)
+        int* tab_q = reinterpret_cast<int*>(tab);
+        float4* tab_w = reinterpret_cast<float4*>(tab + 9 * TM * 4);
+        asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
+        for (int e = tid; e < 9 * TM; e += G_PROD_WARPS * 32) {
+          const int row = e & (TM - 1), tap = e >> 7;
+          const int m = m0 + row;
+          int px, py, b;
+          decode_row(p, m, px, py, b);
+          const bool ok = m < p.P && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
+          float dy = 0.f, dx = 0.f, ml = 0.f;
+          if (ok) {
+            const float* om = p.om + (size_t)m * 32;
+            dy = __ldg(om + 2 * tap); dx = __ldg(om + 2 * tap + 1); ml = __ldg(om + 18 + tap);
           }
-          for (int kc = 0; kc < p.KC; ++kc, ++kc_cnt) {
-            unsigned char* sA = wait_stage(kc_cnt);
+          // padded-frame coordinates (unpadded + 1): the zero border implements "zero outside"
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          float sy = (float)(py - 1 + ky) + dy;
+          float sx = (float)(px - 1 + kx) + dx;
+          const bool in = ok && sy > 0.f && sy < (float)(p.Ho + 1) && sx > 0.f && sx < (float)(p.Wo + 1);
+          const float msk = in ? 1.f / (1.f + __expf(-ml)) : 0.f;
+          sy = in ? sy : 0.f;
+          sx = in ? sx : 0.f;
+          const float yf = floorf(sy), xf = floorf(sx);
+          const float ly = sy - yf, lx = sx - xf, hy = 1.f - ly, hx = 1.f - lx;
+          tab_q[e] = min(b, p.x.B - 1) * iHp * iWp + (int)yf * iWp + (int)xf + p.x.guard;
+          tab_w[e] = make_float4(msk * hy * hx, msk * hy * lx, msk * ly * hx, msk * ly * lx);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
+        for (int kc = 0; kc < p.KC; ++kc) {
+          const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
+          for (int tap = 0; tap < 9; ++tap) {
+            unsigned char* sA = wait_stage();
 #pragma unroll
             for (int ih = 0; ih < 2; ++ih) {
               uint4 v[2][4][NS];
+              float4 w[2];
 #pragma unroll
               for (int ii = 0; ii < 2; ++ii) {
                 const int i = ih * 2 + ii;
+                const int q = tab_q[tap * TM + rr[i]];
+                w[ii] = tab_w[tap * TM + rr[i]];
 #pragma unroll
                 for (int cn = 0; cn < 4; ++cn) {
-                  const long long q = (long long)q00[i] + (cn >> 1) * iWp + (cn & 1);
+                  const int r = q + (cn >> 1) * iWp + (cn & 1);
+                  const unsigned char* src = xk + ((size_t)r << 7) + (((c8 ^ r) & 7) << 4);
 #pragma unroll
-                  for (int pl = 0; pl < NS; ++pl)
-                    v[ii][cn][pl] = __ldg(reinterpret_cast<const uint4*>(p.x.base + pl_offset(p.x, pl, kc, q, c8)));
+                  for (int pl = 0; pl < NS; ++pl) v[ii][cn][pl] = __ldg(reinterpret_cast<const uint4*>(src + pl * plane_bytes));
                 }
               }
 #pragma unroll
@@ -452,126 +518,144 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
                 float o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  o[j] = w00[i] * f[0][j] + w01[i] * f[1][j] + w10[i] * f[2][j] + w11[i] * f[3][j];
+                  o[j] = w[ii].x * f[0][j] + w[ii].y * f[1][j] + w[ii].z * f[2][j] + w[ii].w * f[3][j];
                 uint4 e0, e1;
                 encode8<NS>(o, e0, e1);
-                const uint32_t off = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
-                *reinterpret_cast<uint4*>(sA + off) = e0;
-                if (NS == 2) *reinterpret_cast<uint4*>(sA + a_plane + off) = e1;
+                *reinterpret_cast<uint4*>(sA + soff[i]) = e0;
+                if (NS == 2) *reinterpret_cast<uint4*>(sA + a_plane + soff[i]) = e1;
               }
             }
-            publish(kc_cnt);
-          }
-        }
-      } else if (PROD == PROD_STRIDE) {
-        // 3x3, pad 1, stride s on a PL input: padded input coords of tap (ky,kx) = (oy*s+ky, ox*s+kx)
-        for (int tap = 0; tap < 9; ++tap) {
-          long long q[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            q[i] = (long long)fb[i] + (oy[i] * p.stride + tap / 3) * iWp + ox[i] * p.stride + tap % 3;
-          for (int kc = 0; kc < p.KC; ++kc, ++kc_cnt) {
-            unsigned char* sA = wait_stage(kc_cnt);
-            uint4 v[4][NS];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int pl = 0; pl < NS; ++pl)
-                v[i][pl] = __ldg(reinterpret_cast<const uint4*>(p.x.base + pl_offset(p.x, pl, kc, q[i], c8)));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t off = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
-#pragma unroll
-              for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + off) = v[i][pl];
-            }
-            publish(kc_cnt);
+            publish();
           }
         }
       } else {
-        // SC input: group c8 of K block kb = 16 bytes at byte (anchor + seg_off)*C*2 + (c8 % g)*16
-        const int C2 = p.x.nchunks * 2;   // bytes per input row
-        long long anchor[4];
+        // ---- plain gathers: per tile, the input row of tap (0,0) for each of this thread's rows
+        int anchor[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) anchor[i] = (long long)fb[i] + (long long)(oy[i] * p.stride) * iWp + ox[i] * p.stride;
-        const int seg = c8 / p.seg_groups, within = c8 % p.seg_groups;
-        for (int kb = 0; kb < nkb; ++kb, ++kc_cnt) {
-          unsigned char* sA = wait_stage(kc_cnt);
-          const int so = p.seg_off[kb * 2 + seg];
-          uint4 v[4][NS];
+        for (int i = 0; i < 4; ++i) {
+          int px, py, b;
+          decode_row(p, m0 + rr[i], px, py, b);
+          b = min(b, p.x.B - 1);                          // border / tail rows: any in-bounds address
+          const int oy = min(max(py - 1, 0), p.Ho - 1), ox = min(max(px - 1, 0), p.Wo - 1);
+          anchor[i] = p.x.guard + b * iHp * iWp + oy * p.stride * iWp + ox * p.stride;
+        }
+        if (PROD == PROD_STRIDE) {
+          // 3x3, pad 1, stride s on a PL input: padded input coords of tap (ky,kx) = (oy*s+ky, ox*s+kx)
+          for (int kc = 0; kc < p.KC; ++kc) {
+            const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int toff = (tap / 3) * iWp + tap % 3;
+              uint4 v[4][NS];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < 4; ++i) {
+                const int r = anchor[i] + toff;
+                const unsigned char* src = xk + ((size_t)r << 7) + (((c8 ^ r) & 7) << 4);
 #pragma unroll
-            for (int pl = 0; pl < NS; ++pl) {
-              const unsigned char* src = p.x.base + ((size_t)pl * p.x.rows + p.x.guard + anchor[i] + so) * C2 + within * 16;
-              if (p.vec8) {
-                const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
-                const uint2 b = __ldg(reinterpret_cast<const uint2*>(src + 8));
-                v[i][pl] = make_uint4(a.x, a.y, b.x, b.y);
-              } else {
-                v[i][pl] = __ldg(reinterpret_cast<const uint4*>(src));
+                for (int pl = 0; pl < NS; ++pl) v[i][pl] = __ldg(reinterpret_cast<const uint4*>(src + pl * plane_bytes));
               }
+              unsigned char* sA = wait_stage();
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + soff[i]) = v[i][pl];
+              publish();
             }
           }
+        } else {
+          // SC input: group c8 of K block kb = 16 bytes at (anchor + seg_off[kb][seg]) * C*2 + within*16
+          const int C2 = p.x.nchunks * 2;                 // bytes per input row
+          const size_t sc_plane = (size_t)p.x.rows * C2;
+          const int seg = c8 / p.seg_groups, within = c8 - seg * p.seg_groups;
+          const unsigned char* rowp[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t off = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
+          for (int i = 0; i < 4; ++i) rowp[i] = p.x.base + (size_t)anchor[i] * C2 + within * 16;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int so = p.seg_off[kb * 2 + seg] * C2;
+            uint4 v[4][NS];
 #pragma unroll
-            for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + off) = v[i][pl];
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+              for (int pl = 0; pl < NS; ++pl) {
+                const unsigned char* src = rowp[i] + so + pl * sc_plane;
+                if (p.vec8) {
+                  const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+                  const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(src + 8));
+                  v[i][pl] = make_uint4(a.x, a.y, b2.x, b2.y);
+                } else {
+                  v[i][pl] = __ldg(reinterpret_cast<const uint4*>(src));
+                }
+              }
+            }
+            unsigned char* sA = wait_stage();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + soff[i]) = v[i][pl];
+            publish();
           }
-          publish(kc_cnt);
         }
       }
     }
   } else if (warp == G_PROD_WARPS) {
     // ==================================================================== B loader
     if (lane == 0) {
-      uint32_t kc_cnt = 0;
+      int s = 0;
+      uint32_t ph = 1;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int nt = t % p.n_tiles;
-        for (int kb = 0; kb < nkb; ++kb, ++kc_cnt) {
-          const uint32_t s = kc_cnt % (uint32_t)p.SA;
-          mbar_wait(&empty[s], ((kc_cnt / (uint32_t)p.SA) & 1u) ^ 1u);
+        const unsigned char* wt = p.wpack + (size_t)(t % p.n_tiles) * nkb * b_bytes;
+        // producers walk (kc outer, tap inner) for DCN / STRIDE; packed blocks are (tap, kc)
+        int kc = 0, tap = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int blk = PROD == PROD_SMALLC ? kb : tap * p.KC + kc;
+          mbar_wait(&empty[s], ph);
           mbar_arrive_expect_tx(&full[s], b_bytes);
-          bulk_g2s(smem + (size_t)s * stage_bytes + a_bytes, p.wpack + ((size_t)nt * nkb + kb) * b_bytes, b_bytes, &full[s]);
+          bulk_g2s(smem + (size_t)s * stage_bytes + a_bytes, wt + (size_t)blk * b_bytes, b_bytes, &full[s]);
+          if (++s == p.SA) { s = 0; ph ^= 1u; }
+          if (++tap == 9) { tap = 0; ++kc; }
         }
       }
     }
   } else if (warp == G_PROD_WARPS + 1) {
     // ==================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
-      uint32_t kc_cnt = 0, it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
-        const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
-        mbar_wait(&acc_empty[as], (ause & 1u) ^ 1u);
+    const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+    int s = 0;
+    uint32_t ph = 0, as = 0, accph = 1;
+    const uint32_t smem0 = smem_u32(smem);
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      mbar_wait(&acc_empty[as], accph);
+      tc_fence_after();
+      const uint32_t tacc = tmem + as * acc_stride;
+      int rb = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t tacc = tmem + as * acc_stride;
-        for (int kb = 0; kb < nkb; ++kb, ++kc_cnt) {
-          const uint32_t s = kc_cnt % (uint32_t)p.SA;
-          mbar_wait(&full[s], (kc_cnt / (uint32_t)p.SA) & 1u);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes);
-          issue_kblock<NS>(a0, a_plane, a0 + a_bytes, b_plane, tacc, NT, p.acc_r, idesc, kb);
+        const uint32_t a0 = smem0 + (uint32_t)s * stage_bytes;
+        if (elect_one()) {
+          issue_kblock<NS>(a0, a_plane, a0 + a_bytes, b_plane, tacc, NT, p.acc_r, idesc, kb == 0, rb);
           mma_commit(&empty[s]);
         }
-        mma_commit(&acc_full[as]);
+        rb = next_rb(rb, p.acc_r);
+        __syncwarp();
+        if (++s == p.SA) { s = 0; ph ^= 1u; }
       }
+      if (elect_one()) mma_commit(&acc_full[as]);
+      __syncwarp();
+      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
     }
   } else {
     // ==================================================================== epilogue warps
     const int q = warp & 3;
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    uint32_t as = 0, accph = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      const uint32_t as = p.acc_stages == 2 ? (it & 1u) : 0u;
-      const uint32_t ause = p.acc_stages == 2 ? (it >> 1) : it;
-      mbar_wait(&acc_full[as], ause & 1u);
+      mbar_wait(&acc_full[as], accph);
       tc_fence_after();
-      epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+      if (!(p.dbg & 4))
+        epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
     }
   }
   tc_fence_before();
@@ -616,6 +700,7 @@ static int pick_ntile(int Cout, int NS) {
 // accumulator plan: R hi*hi accumulators (+ D1) per stage; two stages when they fit in 512 columns
 static void plan_acc(ConvP& p, int NS) {
   p.acc_r = NS == 2 ? 3 : 1;
+  while (p.acc_r > 1 && (p.acc_r + NS - 1) * p.NT > 512) --p.acc_r;
   const int per_stage = (p.acc_r + NS - 1) * p.NT;
   p.acc_stages = 2 * per_stage <= 512 ? 2 : 1;
   int need = p.acc_stages * per_stage, c = 32;
@@ -648,9 +733,11 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
 template <int PROD, int NS>
 static int launch_gather(ConvP& p, cudaStream_t st) {
   const int stage = (TM * 128 + p.NT * 128) * NS;
-  const int fixed = 1024 + 512;
+  const int fixed = 1024 + 512 + (PROD == PROD_DCN ? 9 * TM * 20 : 0);
   int SA = (SMEM_LIMIT - fixed) / stage;
-  if (SA > 6) SA = 6;
+  // the gathers live on L1 hits (neighbouring taps / corners touch the same lines): keep the
+  // operand ring short so the unified L1 / shared carve-out leaves a large cache
+  if (SA > 3) SA = 3;
   if (SA < 2) { set_error("conv_gather: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
   p.SA = SA; p.SB = 0;
   const int smem = SA * stage + fixed;
@@ -673,6 +760,8 @@ static bool view_ok(const sgta_planes* v, int layout) {
 using namespace sgta;
 
 extern "C" int sgta_planes_ntile(int Cout, int nplanes) { return pick_ntile(Cout, nplanes); }
+
+extern "C" int sgta_debug_flags(int flags) { int old = g_dbg; g_dbg = flags; return old; }
 
 extern "C" int sgta_planes_guard(int W) { return ((W + 2) * 8 + 160 + 7) & ~7; }
 
@@ -725,6 +814,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
   SGTA_REQUIRE(NT > 0, "sgta_planes_conv: need Cout %% 16 == 0 (got %d)", Cout);
   SGTA_REQUIRE(stride == 1 || stride == 2, "sgta_planes_conv: stride must be 1 or 2");
   ConvP p{};
+  p.dbg = g_dbg;
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
   p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
@@ -734,6 +824,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
   const long long P = (long long)x->B * (Ho + 2) * (Wo + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv: too many pixels");
   p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.m_tiles = cdiv(P, TM);
+  p.magic_wp = magic_u64(Wo + 2); p.magic_hp = magic_u64(Ho + 2);
   int rc = fill_output(p, y, y_f32, ld_f32, Cout, epi, n_valid, x->B, Ho, Wo, NS, "sgta_planes_conv");
   if (rc) return rc;
   if (res) {
@@ -775,12 +866,14 @@ extern "C" int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, cons
   const int NT = pick_ntile(Cout, NS);
   SGTA_REQUIRE(NT > 0, "sgta_planes_conv_sc: need Cout %% 16 == 0 (got %d)", Cout);
   ConvP p{};
+  p.dbg = g_dbg;
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
   p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
   const long long P = (long long)x->B * (Ho + 2) * (Wo + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv_sc: too many pixels");
   p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.m_tiles = cdiv(P, TM);
+  p.magic_wp = magic_u64(Wo + 2); p.magic_hp = magic_u64(Ho + 2);
   int rc = fill_output(p, y, nullptr, 0, Cout, epi, 0, x->B, Ho, Wo, NS, "sgta_planes_conv_sc");
   if (rc) return rc;
   p.in_Wp = x->W + 2 * x->border; p.in_Hp = x->H + 2 * x->border;
@@ -799,6 +892,7 @@ extern "C" int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, co
   const int NT = pick_ntile(Cout, NS);
   SGTA_REQUIRE(NT > 0 && Cout % 64 == 0, "sgta_planes_dcn: need Cout %% 64 == 0 (got %d)", Cout);
   ConvP p{};
+  p.dbg = g_dbg;
   p.x = make_view(x);
   p.om = (const float*)offset_mask;
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
@@ -807,6 +901,7 @@ extern "C" int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, co
   const long long P = (long long)x->B * (x->H + 2) * (x->W + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_dcn: too many pixels");
   p.P = (int)P; p.Ho = x->H; p.Wo = x->W; p.m_tiles = cdiv(P, TM);
+  p.magic_wp = magic_u64(x->W + 2); p.magic_hp = magic_u64(x->H + 2);
   int rc = fill_output(p, y, nullptr, 0, Cout, SGTA_EPI_PL, 0, x->B, x->H, x->W, NS, "sgta_planes_dcn");
   if (rc) return rc;
   p.in_Wp = x->W + 2; p.in_Hp = x->H + 2;

@@ -41,6 +41,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// non-suspending poll (test_wait): for the latency-critical single-thread roles (TMA / MMA issue)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_test_wait(bar, parity)) {
+  }
+}
+
+// one lane of a fully active, converged warp (ELECT): lets ptxas keep tcgen05 / bulk-copy operands
+// in uniform registers instead of wrapping each instruction in a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (UMMA / bulk copy reads)
 __device__ __forceinline__ void fence_async_smem() {
