@@ -166,7 +166,7 @@ typedef struct sgta_planes {
 #define SGTA_EPI_STEM 4     /* Cout == 32 -> SC view with 16 ch: relu(a[c]) + relu(a[16+c])    */
 
 /* performance experiments only (tools/conv_bench.py): bit 0 skip A copies, bit 1 skip B copies,
- * bit 2 skip the epilogue in the planes convolutions (results are then garbage); returns the old value */
+ * bit 2 skip the epilogue, bit 4 skip the MMAs in the planes convolutions (results are then garbage); returns the old value */
 int sgta_debug_flags(int flags);
 /* rows of guard recommended before / after the frames of a W-wide map */
 int sgta_planes_guard(int W);

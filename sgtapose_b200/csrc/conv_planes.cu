@@ -66,6 +66,7 @@ struct ConvP {
   int seg_off[16];       // SMALLC: input row offset of segment j of K block kb at [kb*2 + j]
   int vec8;              // SMALLC: rows are only 8-byte aligned (C = 4)
   unsigned long long magic_wp, magic_hp;   // ceil(2^64 / (Wo+2)), ceil(2^64 / (Ho+2)): exact m / d for m < 2^32
+  int b_resident;        // gather kernels: all weight blocks stay in shared memory (n_tiles == 1)
   int dbg;               // tools/conv_bench.py: 1 = skip A copies, 2 = skip B copies, 4 = skip epilogue math
 };
 
@@ -98,19 +99,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // each.  The tensor core TRUNCATES when it adds a K=16 dot product into the fp32 accumulator
 // (measured: -2.7e-5 relative on an all-positive K=4608 sum), so in the fp32-parity mode the hi*hi
 // products rotate over R accumulators that the epilogue adds in round-to-nearest fp32.
-template <int NS, bool FIRST, int R>
-__device__ __forceinline__ void issue_kblock_impl(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
-                                                  uint32_t tacc, uint32_t NT, uint32_t idesc, int rb) {
+template <int NS> struct AccR { static constexpr int value = NS == 2 ? 3 : 1; };
+
+// rb = (index of this block's first K step) mod R
+template <int NS, bool FIRST>
+__device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
+                                             uint32_t tacc, uint32_t NT, uint32_t idesc, int rb) {
+  constexpr int R = AccR<NS>::value;
   // everything but the 14-bit start-address field of a descriptor is constant: build the four
-  // descriptors once, then only add 2 (= 32 bytes >> 4) per K step -- the single issuing thread
-  // must stay well under one MMA duration (32 clk at N = 64) per instruction
+  // descriptors once, then only add 2 (= 32 bytes >> 4) per K step.  The issuing thread is the
+  // serial bottleneck of small-N tiles (tests/cuda/mma_rate_probe.cu: every branch / loop trip
+  // around the MMAs costs ~100 clk), so callers issue whole groups of K blocks straight-line.
   const uint64_t ah = smem_desc_sw128(a_addr), bh = smem_desc_sw128(b_addr);
   const uint64_t al = smem_desc_sw128(a_addr + a_plane), bl = smem_desc_sw128(b_addr + b_plane);
   const uint32_t tD1 = tacc + (uint32_t)R * NT;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int r = 0;
-    if (R > 1) { r = rb + k; r = r >= R ? r - R : r; }
+    if (R > 1) { r = rb + k; r = r >= R ? r - R : r; r = r >= R ? r - R : r; }
     const uint32_t tD0 = tacc + (uint32_t)r * NT;
     mma_bf16_ss(tD0, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, (FIRST && k < R) ? 0u : 1u);
     if (NS == 2) {
@@ -119,25 +125,21 @@ __device__ __forceinline__ void issue_kblock_impl(uint32_t a_addr, uint32_t a_pl
     }
   }
 }
-// rb = (first K step of this block) mod R, maintained incrementally by the caller
-template <int NS, int R>
-__device__ __forceinline__ void issue_kblock_r(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
-                                               uint32_t tacc, int NT, uint32_t idesc, bool first, int rb) {
-  if (first) issue_kblock_impl<NS, true, R>(a_addr, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0);
-  else issue_kblock_impl<NS, false, R>(a_addr, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb);
-}
-template <int NS>
-__device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
-                                             uint32_t tacc, int NT, int R, uint32_t idesc, bool first, int rb) {
-  switch (R) {
-    case 1: issue_kblock_r<NS, 1>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
-    case 2: issue_kblock_r<NS, 2>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
-    case 3: issue_kblock_r<NS, 3>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
-    default: issue_kblock_r<NS, 4>(a_addr, a_plane, b_addr, b_plane, tacc, NT, idesc, first, rb); break;
+
+// one band of the shift kernel: TAPS K blocks that share an A band (descriptors one row apart),
+// each with its own B slot; slots are released as soon as their MMAs retire
+template <int NS, bool FIRST, int TAPS>
+__device__ __forceinline__ void issue_band(uint32_t a_base, uint32_t a_plane, const uint32_t (&b_addr)[3], uint32_t b_plane,
+                                           uint32_t tacc, uint32_t NT, uint32_t idesc, int rb, uint64_t* const (&b_rel)[3],
+                                           uint64_t* a_rel) {
+#pragma unroll
+  for (int dx = 0; dx < TAPS; ++dx) {
+    if (dx == 0) issue_kblock<NS, FIRST>(a_base, a_plane, b_addr[0], b_plane, tacc, NT, idesc, rb);
+    else issue_kblock<NS, false>(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tacc, NT, idesc, rb + dx);
+    mma_commit(b_rel[dx]);
   }
+  mma_commit(a_rel);
 }
-// 4 K steps per block: the rotation start advances by 4 mod R
-__device__ __forceinline__ int next_rb(int rb, int R) { return R == 3 ? (rb == 2 ? 0 : rb + 1) : 0; }
 
 // ------------------------------------------------------------------------------ epilogue
 // 16 accumulator columns of this thread's row: sum of the R hi*hi accumulators (+ D1 * 2^-11)
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     // ------------------------------------------------------------------ MMA issuer (whole warp
     // walks the loop and waits; one elected lane issues, so operands stay in uniform registers)
     const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+    constexpr int R = AccR<NS>::value;
     int st = 0, sb = 0;
     uint32_t aph = 0, bph = 0;             // parity to wait for on the *_full barriers
     uint32_t as = 0, accph = 1;            // accumulator stage and parity of its acc_empty barrier
@@ -347,31 +350,42 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int m0 = (t / p.n_tiles) * TM;
       mbar_wait(&acc_empty[as], accph);
-      tc_fence_after();
       const uint32_t tacc = tmem + as * acc_stride;
-      int rb = 0;
+      int rb = 0;                          // 1x1: K step rotation start (3x3 bands advance by 12 = 0 mod 3)
       bool first = true;
       for (int kc = 0; kc < p.KC; ++kc) {
         for (int band = 0; band < nb; ++band) {
           const long long s = (long long)p.x.guard + m0 + (p.taps == 9 ? (band - 1) * Wp - 1 : 0);
           const uint32_t off = (uint32_t)(s & 7ll);
-          if (!(p.dbg & 8)) mbar_wait(&a_full[st], aph);
+          mbar_wait(&a_full[st], aph);
           const uint32_t a_base = a_smem + (uint32_t)st * a_stage + off * 128u;
-          for (int dx = 0; dx < ntap_b; ++dx) {
-            if (!(p.dbg & 8)) mbar_wait(&b_full[sb], bph);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_kblock<NS>(a_base + (uint32_t)dx * 128u, a_plane, b_smem + (uint32_t)sb * b_stage, b_plane, tacc, NT,
-                               p.acc_r, idesc, first, rb);
-              mma_commit(&b_empty[sb]);
+          uint32_t b_addr[3];
+          uint64_t* b_rel[3];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            if (dx < ntap_b) {
+              mbar_wait(&b_full[sb], bph);
+              b_addr[dx] = b_smem + (uint32_t)sb * b_stage;
+              b_rel[dx] = &b_empty[sb];
+              if (++sb == p.SB) { sb = 0; bph ^= 1u; }
+            } else {
+              b_addr[dx] = b_smem;
+              b_rel[dx] = &b_empty[0];
             }
-            rb = next_rb(rb, p.acc_r);
-            __syncwarp();
-            first = false;
-            if (++sb == p.SB) { sb = 0; bph ^= 1u; }
           }
-          if (elect_one()) mma_commit(&a_empty[st]);
+          tc_fence_after();
+          if (elect_one()) {
+            if (ntap_b == 3) {
+              if (first) issue_band<NS, true, 3>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+              else issue_band<NS, false, 3>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+            } else {
+              if (first) issue_band<NS, true, 1>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+              else issue_band<NS, false, 1>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb, b_rel, &a_empty[st]);
+            }
+          }
           __syncwarp();
+          first = false;
+          if (R == 3 && ntap_b == 1) rb = rb == 2 ? 0 : rb + 1;
           if (++st == p.SA) { st = 0; aph ^= 1u; }
         }
       }
@@ -408,15 +422,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
   const int NT = p.NT;
   constexpr uint32_t a_plane = TM * 128u, a_bytes = a_plane * NS;
   const uint32_t b_plane = (uint32_t)NT * 128u, b_bytes = b_plane * NS;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.SA * stage_bytes);
+  // ring stage = [A | B]; with resident weights the ring holds A only and all B blocks sit behind it
+  const uint32_t stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
+  unsigned char* sBres = smem + (size_t)p.SA * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBres + (p.b_resident ? (size_t)p.nkb * b_bytes : 0));
   uint64_t *full = bars, *empty = bars + 8, *acc_full = bars + 16, *acc_empty = bars + 18;
+  uint64_t* b_ready = bars + 21;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 32);      // DCN sampling table (9*128*20 B)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < 8; ++s) { mbar_init(&full[s], G_PROD_WARPS + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&full[s], G_PROD_WARPS + (p.b_resident ? 0 : 1)); mbar_init(&empty[s], 1); }
+    mbar_init(b_ready, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_mbar_init();
   }
@@ -528,9 +546,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
             publish();
           }
         }
-      } else {
-        // ---- plain gathers: per tile, the input row of tap (0,0) for each of this thread's rows
-        int anchor[4];
+      }
+    }
+    if (PROD != PROD_DCN) {
+      // ---- plain gathers (STRIDE: PL input, SMALLC: SC input).  The K blocks of all tiles of this
+      // CTA form one flat stream; loads run PD blocks ahead of the shared-memory stores so PD
+      // blocks of global-load latency overlap per warp (8 warps per SM cannot hide it otherwise).
+      constexpr int PD = 3;
+      uint4 v[PD][4][NS];
+      const int C2 = p.x.nchunks * 2;                   // SC: bytes per input row
+      const size_t sc_plane = (size_t)p.x.rows * C2;
+      const int seg = c8 / p.seg_groups, within = c8 - seg * p.seg_groups;
+      const int my_tiles = blockIdx.x < total ? (total - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      const long long nblk = (long long)my_tiles * nkb;
+      int lt = blockIdx.x, lkb = 0;                     // load cursor: tile, K block inside the tile
+      int anchor[4] = {0, 0, 0, 0};
+      auto set_tile = [&](int t) {
+        const int m0 = (t / p.n_tiles) * TM;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           int px, py, b;
@@ -539,59 +571,68 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
           const int oy = min(max(py - 1, 0), p.Ho - 1), ox = min(max(px - 1, 0), p.Wo - 1);
           anchor[i] = p.x.guard + b * iHp * iWp + oy * p.stride * iWp + ox * p.stride;
         }
+      };
+      auto load_block = [&](uint4 (&dst)[4][NS]) {
+        if (lkb == 0) set_tile(lt);
         if (PROD == PROD_STRIDE) {
-          // 3x3, pad 1, stride s on a PL input: padded input coords of tap (ky,kx) = (oy*s+ky, ox*s+kx)
-          for (int kc = 0; kc < p.KC; ++kc) {
-            const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
-            for (int tap = 0; tap < 9; ++tap) {
-              const int toff = (tap / 3) * iWp + tap % 3;
-              uint4 v[4][NS];
+          // 3x3, pad 1, stride s: padded input coords of tap (ky,kx) = (oy*s+ky, ox*s+kx); kc outer
+          const int kc = lkb / 9, tap = lkb - kc * 9;
+          const int toff = (tap / 3) * iWp + tap % 3;
+          const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int r = anchor[i] + toff;
-                const unsigned char* src = xk + ((size_t)r << 7) + (((c8 ^ r) & 7) << 4);
+          for (int i = 0; i < 4; ++i) {
+            const int r = anchor[i] + toff;
+            const unsigned char* src = xk + ((size_t)r << 7) + (((c8 ^ r) & 7) << 4);
 #pragma unroll
-                for (int pl = 0; pl < NS; ++pl) v[i][pl] = __ldg(reinterpret_cast<const uint4*>(src + pl * plane_bytes));
-              }
-              unsigned char* sA = wait_stage();
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + soff[i]) = v[i][pl];
-              publish();
-            }
+            for (int pl = 0; pl < NS; ++pl) dst[i][pl] = __ldg(reinterpret_cast<const uint4*>(src + pl * plane_bytes));
           }
         } else {
-          // SC input: group c8 of K block kb = 16 bytes at (anchor + seg_off[kb][seg]) * C*2 + within*16
-          const int C2 = p.x.nchunks * 2;                 // bytes per input row
-          const size_t sc_plane = (size_t)p.x.rows * C2;
-          const int seg = c8 / p.seg_groups, within = c8 - seg * p.seg_groups;
-          const unsigned char* rowp[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rowp[i] = p.x.base + (size_t)anchor[i] * C2 + within * 16;
-          for (int kb = 0; kb < nkb; ++kb) {
-            const int so = p.seg_off[kb * 2 + seg] * C2;
-            uint4 v[4][NS];
+          if (p.vec8) {
+            // C = 4 (rows only 8-byte aligned): group c8 = [pixel c8 of segment 0 | pixel c8 of segment 1],
+            // so the 8 lanes of a row read two contiguous 64-byte runs (the weight matrix uses the same order)
+            const int so0 = p.seg_off[lkb * 2], so1 = p.seg_off[lkb * 2 + 1];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+              const unsigned char* s0 = p.x.base + (size_t)(anchor[i] + so0) * C2 + c8 * 8;
+              const unsigned char* s1 = p.x.base + (size_t)(anchor[i] + so1) * C2 + c8 * 8;
 #pragma unroll
               for (int pl = 0; pl < NS; ++pl) {
-                const unsigned char* src = rowp[i] + so + pl * sc_plane;
-                if (p.vec8) {
-                  const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
-                  const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(src + 8));
-                  v[i][pl] = make_uint4(a.x, a.y, b2.x, b2.y);
-                } else {
-                  v[i][pl] = __ldg(reinterpret_cast<const uint4*>(src));
-                }
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(s0 + pl * sc_plane));
+                const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(s1 + pl * sc_plane));
+                dst[i][pl] = make_uint4(a.x, a.y, b2.x, b2.y);
               }
             }
-            unsigned char* sA = wait_stage();
+          } else {
+            // group c8 of K block kb = 16 bytes at (anchor + seg_off[kb][seg]) * C*2 + within*16
+            const int so = p.seg_off[lkb * 2 + seg];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
+              const unsigned char* src0 = p.x.base + (size_t)(anchor[i] + so) * C2 + within * 16;
 #pragma unroll
-              for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + soff[i]) = v[i][pl];
-            publish();
+              for (int pl = 0; pl < NS; ++pl) dst[i][pl] = __ldg(reinterpret_cast<const uint4*>(src0 + pl * sc_plane));
+            }
+          }
+        }
+        if (++lkb == nkb) { lkb = 0; lt += gridDim.x; }
+      };
+      auto store_block = [&](const uint4 (&src)[4][NS]) {
+        unsigned char* sA = wait_stage();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + soff[i]) = src[i][pl];
+        publish();
+      };
+      if (p.dbg & 1) {
+        for (long long j = 0; j < nblk; ++j) { wait_stage(); publish(); }
+      } else {
+        for (long long j0 = 0; j0 < nblk + PD - 1; j0 += PD) {
+#pragma unroll
+          for (int d = 0; d < PD; ++d) {
+            const long long j = j0 + d;
+            // slot d holds block j; it was stored (as block j - PD) PD-1 iterations ago
+            if (j >= PD - 1 && j - (PD - 1) < nblk) store_block(v[(d + 1) % PD]);
+            if (j < nblk) load_block(v[d]);
           }
         }
       }
@@ -599,43 +640,57 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
   } else if (warp == G_PROD_WARPS) {
     // ==================================================================== B loader
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 1;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const unsigned char* wt = p.wpack + (size_t)(t % p.n_tiles) * nkb * b_bytes;
-        // producers walk (kc outer, tap inner) for DCN / STRIDE; packed blocks are (tap, kc)
-        int kc = 0, tap = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int blk = PROD == PROD_SMALLC ? kb : tap * p.KC + kc;
-          mbar_wait(&empty[s], ph);
-          mbar_arrive_expect_tx(&full[s], b_bytes);
-          bulk_g2s(smem + (size_t)s * stage_bytes + a_bytes, wt + (size_t)blk * b_bytes, b_bytes, &full[s]);
-          if (++s == p.SA) { s = 0; ph ^= 1u; }
-          if (++tap == 9) { tap = 0; ++kc; }
+      if (p.b_resident) {
+        // weights are loaded once per CTA; packed block order (tap, kc) is kept
+        mbar_arrive_expect_tx(b_ready, (uint32_t)nkb * b_bytes);
+        for (int kb = 0; kb < nkb; ++kb)
+          bulk_g2s(sBres + (size_t)kb * b_bytes, p.wpack + (size_t)kb * b_bytes, b_bytes, b_ready);
+      } else {
+        int s = 0;
+        uint32_t ph = 1;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+          const unsigned char* wt = p.wpack + (size_t)(t % p.n_tiles) * nkb * b_bytes;
+          // producers walk (kc outer, tap inner) for DCN / STRIDE; packed blocks are (tap, kc)
+          int kc = 0, tap = 0;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int blk = PROD == PROD_SMALLC ? kb : tap * p.KC + kc;
+            mbar_wait(&empty[s], ph);
+            mbar_arrive_expect_tx(&full[s], b_bytes);
+            bulk_g2s(smem + (size_t)s * stage_bytes + a_bytes, wt + (size_t)blk * b_bytes, b_bytes, &full[s]);
+            if (++s == p.SA) { s = 0; ph ^= 1u; }
+            if (++tap == 9) { tap = 0; ++kc; }
+          }
         }
       }
     }
   } else if (warp == G_PROD_WARPS + 1) {
     // ==================================================================== MMA issuer
     const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+    constexpr int R = AccR<NS>::value;
     int s = 0;
     uint32_t ph = 0, as = 0, accph = 1;
-    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t smem0 = smem_u32(smem), bres0 = smem_u32(sBres);
+    if (p.b_resident) mbar_wait(b_ready, 0);
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       mbar_wait(&acc_empty[as], accph);
-      tc_fence_after();
       const uint32_t tacc = tmem + as * acc_stride;
-      int rb = 0;
+      int rb = 0, kc = 0, tap = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a0 = smem0 + (uint32_t)s * stage_bytes;
+        const int blk = PROD == PROD_SMALLC ? kb : tap * p.KC + kc;
+        const uint32_t b0 = p.b_resident ? bres0 + (uint32_t)blk * b_bytes : a0 + a_bytes;
+        if (++tap == 9) { tap = 0; ++kc; }
         if (elect_one()) {
-          issue_kblock<NS>(a0, a_plane, a0 + a_bytes, b_plane, tacc, NT, p.acc_r, idesc, kb == 0, rb);
+          if (!(p.dbg & 16)) {
+            if (kb == 0) issue_kblock<NS, true>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, 0);
+            else issue_kblock<NS, false>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, rb);
+          }
           mma_commit(&empty[s]);
         }
-        rb = next_rb(rb, p.acc_r);
         __syncwarp();
+        if (R == 3) rb = rb == 2 ? 0 : rb + 1;
         if (++s == p.SA) { s = 0; ph ^= 1u; }
       }
       if (elect_one()) mma_commit(&acc_full[as]);
@@ -699,8 +754,7 @@ static int pick_ntile(int Cout, int NS) {
 }
 // accumulator plan: R hi*hi accumulators (+ D1) per stage; two stages when they fit in 512 columns
 static void plan_acc(ConvP& p, int NS) {
-  p.acc_r = NS == 2 ? 3 : 1;
-  while (p.acc_r > 1 && (p.acc_r + NS - 1) * p.NT > 512) --p.acc_r;
+  p.acc_r = NS == 2 ? 3 : 1;          // == AccR<NS>::value; (3 + 1) * 128 columns still fit the 512 of TMEM
   const int per_stage = (p.acc_r + NS - 1) * p.NT;
   p.acc_stages = 2 * per_stage <= 512 ? 2 : 1;
   int need = p.acc_stages * per_stage, c = 32;
@@ -732,15 +786,22 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
 
 template <int PROD, int NS>
 static int launch_gather(ConvP& p, cudaStream_t st) {
-  const int stage = (TM * 128 + p.NT * 128) * NS;
+  const int a_bytes = TM * 128 * NS, b_bytes = p.NT * 128 * NS;
   const int fixed = 1024 + 512 + (PROD == PROD_DCN ? 9 * TM * 20 : 0);
-  int SA = (SMEM_LIMIT - fixed) / stage;
+  // weights resident in shared memory when one CTA sees a single N tile and they leave room for
+  // >= 2 A stages: no per-K-block weight copy (a single thread's bulk copies serialise, ~530 clk each)
+  p.b_resident = p.n_tiles == 1 && fixed + p.nkb * b_bytes + 2 * a_bytes <= SMEM_LIMIT;
+  const int stage = p.b_resident ? a_bytes : a_bytes + b_bytes;
+  const int avail = SMEM_LIMIT - fixed - (p.b_resident ? p.nkb * b_bytes : 0);
+  int SA = avail / stage;
   // the gathers live on L1 hits (neighbouring taps / corners touch the same lines): keep the
   // operand ring short so the unified L1 / shared carve-out leaves a large cache
+  // (consuming G > 1 stages per issue group helps the MMA warp of the small-N layers but the
+  // deeper ring it needs evicts the L1 the producers live on: measured slower, so G stays 1)
   if (SA > 3) SA = 3;
   if (SA < 2) { set_error("conv_gather: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
   p.SA = SA; p.SB = 0;
-  const int smem = SA * stage + fixed;
+  const int smem = SA * stage + fixed + (p.b_resident ? p.nkb * b_bytes : 0);
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;

@@ -188,7 +188,11 @@ class ScConvSpec:
                     kx = kx0 + pp
                     if kx >= k:
                         continue
-                    kbase = j * (seg_bytes // 2) + pp * C + cin_off
+                    if C == 4:
+                        # 8-byte pixels: the kernel interleaves the two segments of a K block per pixel
+                        kbase = (j // 2) * 64 + pp * 8 + (j % 2) * 4 + cin_off
+                    else:
+                        kbase = j * (seg_bytes // 2) + pp * C + cin_off
                     wm[o0:o0 + co, kbase:kbase + ci] = w[:, :, ky, kx].float()
             o0 += co
         Cp = pad_to(Cout, 16)

@@ -12,11 +12,11 @@ template <int N>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int nacc, int shifted, int commit_every, unsigned long long* out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar, dummy;
+  __shared__ uint64_t bar, dummy, ready;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (160 * 128 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&dummy, 1 << 20); fence_mbar_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&dummy, 1 << 20); mbar_init(&ready, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc<512>(&slot);
   fence_async_smem();
   tc_fence_before();
@@ -36,9 +36,9 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int nacc, int s
           mma_bf16_ss(tmem + (uint32_t)(r * N), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
           r = r + 1 == nacc ? 0 : r + 1;
         }
-        if (commit_every && (it % commit_every) == 0) mma_commit(&dummy);
+        if (commit_every == 101 || commit_every == 102) mma_commit(&dummy);
       }
-      if (commit_every < 0) tc_fence_after();
+      if (commit_every == 100 || commit_every == 101) { mbar_wait(&ready, 1); tc_fence_after(); }
       r = (r + 0);
       __syncwarp();
     }
@@ -73,7 +73,7 @@ void run(int nacc, int commit_every, unsigned long long* d) {
 int main() {
   unsigned long long* d;
   cudaMalloc(&d, 148 * 8);
-  for (int ce : {0, 1, 2, 4, -1}) {
+  for (int ce : {0, 100, 102, 101}) {
     run<64>(1, ce, d); run<128>(1, ce, d); run<256>(1, ce, d);
   }
   return 0;
