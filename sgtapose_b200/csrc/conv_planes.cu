@@ -102,10 +102,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 template <int NS> struct AccR { static constexpr int value = NS == 2 ? 3 : 1; };
 
 // rb = (index of this block's first K step) mod R
-template <int NS, bool FIRST>
+template <int NS, bool FIRST, int R = AccR<NS>::value>
 __device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
                                              uint32_t tacc, uint32_t NT, uint32_t idesc, int rb) {
-  constexpr int R = AccR<NS>::value;
   // everything but the 14-bit start-address field of a descriptor is constant: build the four
   // descriptors once, then only add 2 (= 32 bytes >> 4) per K step.  The issuing thread is the
   // serial bottleneck of small-N tiles (tests/cuda/mma_rate_probe.cu: every branch / loop trip
@@ -128,14 +127,14 @@ __device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, 
 
 // one band of the shift kernel: TAPS K blocks that share an A band (descriptors one row apart),
 // each with its own B slot; slots are released as soon as their MMAs retire
-template <int NS, bool FIRST, int TAPS>
+template <int NS, bool FIRST, int TAPS, int R>
 __device__ __forceinline__ void issue_band(uint32_t a_base, uint32_t a_plane, const uint32_t (&b_addr)[3], uint32_t b_plane,
                                            uint32_t tacc, uint32_t NT, uint32_t idesc, int rb, uint64_t* const (&b_rel)[3],
                                            uint64_t* a_rel) {
 #pragma unroll
   for (int dx = 0; dx < TAPS; ++dx) {
-    if (dx == 0) issue_kblock<NS, FIRST>(a_base, a_plane, b_addr[0], b_plane, tacc, NT, idesc, rb);
-    else issue_kblock<NS, false>(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tacc, NT, idesc, rb + dx);
+    if (dx == 0) issue_kblock<NS, FIRST, R>(a_base, a_plane, b_addr[0], b_plane, tacc, NT, idesc, rb);
+    else issue_kblock<NS, false, R>(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tacc, NT, idesc, rb + dx);
     mma_commit(b_rel[dx]);
   }
   mma_commit(a_rel);
@@ -250,6 +249,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int
   }
 }
 
+// explicit shared-memory accesses (pointers derived from the dynamic smem base otherwise compile to
+// generic LD / ST)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ unsigned char* align1024(unsigned char* p) {
   return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
@@ -263,7 +273,7 @@ __device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, int cols) {
 }
 
 // =============================================================================== shift kernel
-template <int NS>
+template <int NS, int R>
 __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_constant__ ConvP p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align1024(smem_raw);
@@ -342,7 +352,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     // ------------------------------------------------------------------ MMA issuer (whole warp
     // walks the loop and waits; one elected lane issues, so operands stay in uniform registers)
     const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
-    constexpr int R = AccR<NS>::value;
     int st = 0, sb = 0;
     uint32_t aph = 0, bph = 0;             // parity to wait for on the *_full barriers
     uint32_t as = 0, accph = 1;            // accumulator stage and parity of its acc_empty barrier
@@ -376,11 +385,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
           tc_fence_after();
           if (elect_one()) {
             if (ntap_b == 3) {
-              if (first) issue_band<NS, true, 3>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
-              else issue_band<NS, false, 3>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+              if (first) issue_band<NS, true, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+              else issue_band<NS, false, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
             } else {
-              if (first) issue_band<NS, true, 1>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
-              else issue_band<NS, false, 1>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb, b_rel, &a_empty[st]);
+              if (first) issue_band<NS, true, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+              else issue_band<NS, false, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb, b_rel, &a_empty[st]);
             }
           }
           __syncwarp();
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     uint32_t as = 0, accph = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      mbar_wait(&acc_full[as], accph);
+      mbar_wait_backoff(&acc_full[as], accph);
       tc_fence_after();
       if (!(p.dbg & 4))
         epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
@@ -429,7 +438,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
   uint64_t *full = bars, *empty = bars + 8, *acc_full = bars + 16, *acc_empty = bars + 18;
   uint64_t* b_ready = bars + 21;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 32);      // DCN sampling table (9*128*20 B)
+  unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 32);      // DCN sampling table (9*128*32 B)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -476,10 +485,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int m0 = (t / p.n_tiles) * TM;
       if (PROD == PROD_DCN) {
-        // ---- per tile: sampling table in shared memory (one entry per (tap, row)): corner-00 row
-        // index and the four mask*bilinear weights; every lane of a row reads it back (broadcast)
-        int* tab_q = reinterpret_cast<int*>(tab);
-        float4* tab_w = reinterpret_cast<float4*>(tab + 9 * TM * 4);
+        // ---- per tile: sampling table in shared memory, one entry per (tap, row): the byte offsets
+        // of the four corner rows inside a chunk (16-byte group 0, swizzle folded in: a lane only
+        // XORs its own group index) and the four mask*bilinear weights; every lane of a row reads
+        // them back (broadcast).  The producers are instruction-bound (tools/dcn_bench.py: the same
+        // time with the global loads removed), so everything row-invariant lives here.
+        uint4* tab_o = reinterpret_cast<uint4*>(tab);
+        float4* tab_w = reinterpret_cast<float4*>(tab + 9 * TM * 16);
         asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
         for (int e = tid; e < 9 * TM; e += G_PROD_WARPS * 32) {
           const int row = e & (TM - 1), tap = e >> 7;
@@ -502,14 +514,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
           sx = in ? sx : 0.f;
           const float yf = floorf(sy), xf = floorf(sx);
           const float ly = sy - yf, lx = sx - xf, hy = 1.f - ly, hx = 1.f - lx;
-          tab_q[e] = min(b, p.x.B - 1) * iHp * iWp + (int)yf * iWp + (int)xf + p.x.guard;
+          const uint32_t r0 = (uint32_t)(min(b, p.x.B - 1) * iHp * iWp + (int)yf * iWp + (int)xf + p.x.guard);
+          const uint32_t r1 = r0 + 1u, r2 = r0 + (uint32_t)iWp, r3 = r2 + 1u;
+          tab_o[e] = make_uint4((r0 << 7) | ((r0 & 7u) << 4), (r1 << 7) | ((r1 & 7u) << 4),
+                                (r2 << 7) | ((r2 & 7u) << 4), (r3 << 7) | ((r3 & 7u) << 4));
           tab_w[e] = make_float4(msk * hy * hx, msk * hy * lx, msk * ly * hx, msk * ly * lx);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
+        const uint32_t gx = (uint32_t)c8 << 4;
+        const uint32_t tab_s = smem_u32(tab);
         for (int kc = 0; kc < p.KC; ++kc) {
           const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
+          const unsigned char* xl = xk + plane_bytes;
           for (int tap = 0; tap < 9; ++tap) {
-            unsigned char* sA = wait_stage();
+            const uint32_t sA_s = smem_u32(wait_stage());
+            if (p.dbg & 1) { publish(); continue; }
 #pragma unroll
             for (int ih = 0; ih < 2; ++ih) {
               uint4 v[2][4][NS];
@@ -517,30 +536,73 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
 #pragma unroll
               for (int ii = 0; ii < 2; ++ii) {
                 const int i = ih * 2 + ii;
-                const int q = tab_q[tap * TM + rr[i]];
-                w[ii] = tab_w[tap * TM + rr[i]];
+                const uint4 o4 = lds128(tab_s + (uint32_t)(tap * TM + rr[i]) * 16u);
+                const uint4 w4 = lds128(tab_s + (uint32_t)(9 * TM + tap * TM + rr[i]) * 16u);
+                w[ii] = make_float4(__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w));
+                const uint32_t off[4] = {o4.x ^ gx, o4.y ^ gx, o4.z ^ gx, o4.w ^ gx};
 #pragma unroll
                 for (int cn = 0; cn < 4; ++cn) {
-                  const int r = q + (cn >> 1) * iWp + (cn & 1);
-                  const unsigned char* src = xk + ((size_t)r << 7) + (((c8 ^ r) & 7) << 4);
-#pragma unroll
-                  for (int pl = 0; pl < NS; ++pl) v[ii][cn][pl] = __ldg(reinterpret_cast<const uint4*>(src + pl * plane_bytes));
+                  v[ii][cn][0] = __ldg(reinterpret_cast<const uint4*>(xk + off[cn]));
+                  if (NS == 2) v[ii][cn][NS - 1] = __ldg(reinterpret_cast<const uint4*>(xl + off[cn]));
                 }
               }
 #pragma unroll
               for (int ii = 0; ii < 2; ++ii) {
                 const int i = ih * 2 + ii;
-                float f[4][8];
+                const float wc[4] = {w[ii].x, w[ii].y, w[ii].z, w[ii].w};
+                uint4 e0, e1 = make_uint4(0, 0, 0, 0);
+                if (NS == 2) {
+                  // hi plane blended in fp32; lo plane (a 2^-11-scaled correction) blended in packed
+                  // fp16 (its rounding lands at 2^-21 relative); the convex combination of fp16-range
+                  // values needs no clamp before the re-split
+                  float H[8];
+                  __half2 L[4];
 #pragma unroll
-                for (int cn = 0; cn < 4; ++cn) decode8<NS>(v[ii][cn][0], v[ii][cn][NS - 1], f[cn]);
-                float o[8];
+                  for (int cn = 0; cn < 4; ++cn) {
+                    const uint32_t hv[4] = {v[ii][cn][0].x, v[ii][cn][0].y, v[ii][cn][0].z, v[ii][cn][0].w};
+                    const uint32_t lv[4] = {v[ii][cn][1].x, v[ii][cn][1].y, v[ii][cn][1].z, v[ii][cn][1].w};
+                    const __half2 wh = __float2half2_rn(wc[cn]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  o[j] = w[ii].x * f[0][j] + w[ii].y * f[1][j] + w[ii].z * f[2][j] + w[ii].w * f[3][j];
-                uint4 e0, e1;
-                encode8<NS>(o, e0, e1);
-                *reinterpret_cast<uint4*>(sA + soff[i]) = e0;
-                if (NS == 2) *reinterpret_cast<uint4*>(sA + a_plane + soff[i]) = e1;
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 hf = unpack_h2(hv[j]);
+                      const __half2 lh = *reinterpret_cast<const __half2*>(&lv[j]);
+                      if (cn == 0) {
+                        H[2 * j] = wc[0] * hf.x; H[2 * j + 1] = wc[0] * hf.y;
+                        L[j] = __hmul2(wh, lh);
+                      } else {
+                        H[2 * j] = fmaf(wc[cn], hf.x, H[2 * j]); H[2 * j + 1] = fmaf(wc[cn], hf.y, H[2 * j + 1]);
+                        L[j] = __hfma2(wh, lh, L[j]);
+                      }
+                    }
+                  }
+                  uint32_t eh[4], el[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 lf = __half22float2(L[j]);
+                    const float a = fmaf(lf.x, LO_INV, H[2 * j]), b2 = fmaf(lf.y, LO_INV, H[2 * j + 1]);
+                    const __half2 h = __floats2half2_rn(a, b2);
+                    const float2 hb = __half22float2(h);
+                    eh[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    el[j] = pack_h2((a - hb.x) * LO_SCALE, (b2 - hb.y) * LO_SCALE);
+                  }
+                  e0 = make_uint4(eh[0], eh[1], eh[2], eh[3]);
+                  e1 = make_uint4(el[0], el[1], el[2], el[3]);
+                } else {
+                  float o[8];
+#pragma unroll
+                  for (int cn = 0; cn < 4; ++cn) {
+                    const uint32_t bv[4] = {v[ii][cn][0].x, v[ii][cn][0].y, v[ii][cn][0].z, v[ii][cn][0].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 f = unpack_b2(bv[j]);
+                      if (cn == 0) { o[2 * j] = wc[0] * f.x; o[2 * j + 1] = wc[0] * f.y; }
+                      else { o[2 * j] = fmaf(wc[cn], f.x, o[2 * j]); o[2 * j + 1] = fmaf(wc[cn], f.y, o[2 * j + 1]); }
+                    }
+                  }
+                  e0 = make_uint4(pack_b2(o[0], o[1]), pack_b2(o[2], o[3]), pack_b2(o[4], o[5]), pack_b2(o[6], o[7]));
+                }
+                sts128(sA_s + soff[i], e0);
+                if (NS == 2) sts128(sA_s + a_plane + soff[i], e1);
               }
             }
             publish();
@@ -703,7 +765,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
     uint32_t as = 0, accph = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      mbar_wait(&acc_full[as], accph);
+      mbar_wait_backoff(&acc_full[as], accph);
       tc_fence_after();
       if (!(p.dbg & 4))
         epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
@@ -753,8 +815,11 @@ static int pick_ntile(int Cout, int NS) {
   return nt;
 }
 // accumulator plan: R hi*hi accumulators (+ D1) per stage; two stages when they fit in 512 columns
-static void plan_acc(ConvP& p, int NS) {
-  p.acc_r = NS == 2 ? 3 : 1;          // == AccR<NS>::value; (3 + 1) * 128 columns still fit the 512 of TMEM
+// short_k: the truncation bias grows with the number of K steps (tools/acc_probe.py); a K <= 576 sum
+// stays below 4e-6 relative without rotation, and R = 1 lets a 128-wide N tile keep TWO accumulator
+// stages so the epilogue overlaps the next tile's MMAs (the 64 -> 768 head convolution)
+static void plan_acc(ConvP& p, int NS, bool short_k = false) {
+  p.acc_r = NS == 2 ? (short_k ? 1 : 3) : 1;   // (3 + 1) * 128 columns still fit the 512 of TMEM
   const int per_stage = (p.acc_r + NS - 1) * p.NT;
   p.acc_stages = 2 * per_stage <= 512 ? 2 : 1;
   int need = p.acc_stages * per_stage, c = 32;
@@ -779,15 +844,20 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
-  cudaFuncSetAttribute(conv_shift_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  conv_shift_kernel<NS><<<grid, S_THREADS, smem, st>>>(p);
+  if (p.acc_r == 1) {
+    cudaFuncSetAttribute(conv_shift_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_shift_kernel<NS, 1><<<grid, S_THREADS, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(conv_shift_kernel<NS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_shift_kernel<NS, 3><<<grid, S_THREADS, smem, st>>>(p);
+  }
   return check_launch("conv_shift_kernel");
 }
 
 template <int PROD, int NS>
 static int launch_gather(ConvP& p, cudaStream_t st) {
   const int a_bytes = TM * 128 * NS, b_bytes = p.NT * 128 * NS;
-  const int fixed = 1024 + 512 + (PROD == PROD_DCN ? 9 * TM * 20 : 0);
+  const int fixed = 1024 + 512 + (PROD == PROD_DCN ? 9 * TM * 32 : 0);
   // weights resident in shared memory when one CTA sees a single N tile and they leave room for
   // >= 2 A stages: no per-K-block weight copy (a single thread's bulk copies serialise, ~530 clk each)
   p.b_resident = p.n_tiles == 1 && fixed + p.nkb * b_bytes + 2 * a_bytes <= SMEM_LIMIT;
@@ -902,6 +972,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
     if (stride == 1) {
       SGTA_REQUIRE(ksize == 1 || ksize == 3, "sgta_planes_conv: PL stride-1 kernels are 1x1 or 3x3");
       p.taps = ksize * ksize; p.nkb = p.taps * p.KC; p.a_rows = ksize == 3 ? 144 : 136;
+      if (NS == 2 && NT == 128 && p.nkb <= 9) plan_acc(p, NS, true);
       const int Wp = x->W + 2;
       SGTA_REQUIRE(x->guard >= Wp + 1 + 8 && x->rows >= (int64_t)x->guard + (int64_t)p.m_tiles * TM + Wp + 16 + 8,
                    "sgta_planes_conv: input guard rows too small for the halo");

@@ -41,6 +41,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// wait with back-off: for warps that wait for whole tiles (epilogue), so their polling does not
+// take issue slots from the producer warps of the same SM sub-partition
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 // non-suspending poll (test_wait): for the latency-critical single-thread roles (TMA / MMA issue)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
