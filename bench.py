@@ -148,6 +148,8 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
     B = args.batch
+    if args.dbg:
+        _lib.load().sgta_debug_flags(args.dbg)
     host = [t.pin_memory() for t in synth.synthetic_inputs(B, S, seed=317 + rank, frame=1)]
     resident = [t.to(dev, non_blocking=True) for t in host]
     h2d = sum(t.numel() * t.element_size() for t in host)
@@ -317,6 +319,7 @@ def main():
     ap.add_argument("--engine", default="graph", choices=["graph", "eager"])
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dbg", type=int, default=0, help="sgta_debug_flags value (kernel experiments; 0 for any reported number)")
     ap.add_argument("--profile-pass", action="store_true",
                     help="run one un-graphed step inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()

@@ -39,7 +39,8 @@ constexpr int G_PROD_WARPS = 8;
 constexpr int G_THREADS = (G_PROD_WARPS + 2 + 4) * 32;   // producers, B loader, MMA, 4 epilogue warps
 constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
                                                          // each, tests/cuda/tma_bw_probe.cu): spread them over 4
-constexpr int S_THREADS = (S_TMA_WARPS + 1 + 4) * 32;    // TMA warps, MMA, 4 epilogue warps
+constexpr int S_EPI_NH = 1;                              // epilogue warps per TMEM lane quadrant
+constexpr int S_THREADS = (S_TMA_WARPS + 1 + 4 * S_EPI_NH) * 32;    // TMA warps, MMA, epilogue warps
 
 enum { PROD_DCN = 0, PROD_STRIDE = 1, PROD_SMALLC = 2 };
 
@@ -67,6 +68,7 @@ struct ConvP {
   int vec8;              // SMALLC: rows are only 8-byte aligned (C = 4)
   unsigned long long magic_wp, magic_hp;   // ceil(2^64 / (Wo+2)), ceil(2^64 / (Ho+2)): exact m / d for m < 2^32
   int b_resident;        // gather kernels: all weight blocks stay in shared memory (n_tiles == 1)
+  int stg_bytes;         // EPI_PL: bytes of the epilogue's store staging tile (one 64-channel chunk x planes) at the head of smem
   int dbg;               // tools/conv_bench.py: 1 = skip A copies, 2 = skip B copies, 4 = skip epilogue math
 };
 
@@ -140,6 +142,28 @@ __device__ __forceinline__ void issue_band(uint32_t a_base, uint32_t a_plane, co
   mma_commit(a_rel);
 }
 
+// explicit shared-memory accesses (pointers derived from the dynamic smem base otherwise compile to
+// generic LD / ST)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// shared -> global bulk copy (TMA engine), bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+template <int NH>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, %0;" ::"n"(NH * 128) : "memory"); }
+
 // ------------------------------------------------------------------------------ epilogue
 // 16 accumulator columns of this thread's row: sum of the R hi*hi accumulators (+ D1 * 2^-11)
 template <int NS>
@@ -164,21 +188,140 @@ __device__ __forceinline__ void read_acc16(uint32_t tacc, int NT, int R, int c0,
 }
 
 // One thread = one output row (TMEM lane).  tacc: TMEM address of D0 incl. the lane base.
+// stage_s != 0 (EPI_PL, tile fully inside the view): rows are written to a shared-memory image of the
+// output tile (same swizzle as global) and ONE thread bulk-stores each 16 KB chunk-plane; border rows
+// are stored as zeros, which is what they hold anyway.
+// The epilogue is instruction-latency bound (one warp per SM sub-partition walks ~300 dependent
+// instructions per 16 columns), so the shift kernel runs NH = 2 warps per TMEM lane quadrant: warp
+// `half` takes its share of the 16-column groups of every 64-column chunk.
+struct EpiRow {
+  int m, px, py, b;
+  bool inP, valid, has_res, staged;
+  uint32_t srow, sxor;
+};
+
+// accumulator columns [c0, c0+16) of this thread's row: sum of the R hi*hi accumulators (+ D1 * 2^-11);
+// all TMEM reads are issued back to back
 template <int NS>
-__device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row) {
+__device__ __forceinline__ void epi_read(const ConvP& p, uint32_t tacc, int c0, float (&o)[16]) {
+  const int NT = p.NT, R = p.acc_r;
+  uint32_t d0[16], d1[16], d2[16], dl[16];
+  tmem_ld16(tacc + (uint32_t)c0, d0);
+  if (R == 3) {
+    tmem_ld16(tacc + (uint32_t)(NT + c0), d1);
+    tmem_ld16(tacc + (uint32_t)(2 * NT + c0), d2);
+  }
+  if (NS == 2) tmem_ld16(tacc + (uint32_t)(R * NT + c0), dl);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(d0[j]);
+  if (R == 3) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { o[j] += __uint_as_float(d1[j]); o[j] += __uint_as_float(d2[j]); }
+  }
+  if (NS == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = fmaf(__uint_as_float(dl[j]), LO_INV, o[j]);
+  }
+}
+
+// scale / shift / residual / activation / store of 16 columns held in registers
+template <int NS>
+__device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int n, float (&o)[16]) {
+  uint4 rv[2][NS];
+  if (e.has_res) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ch = n + 8 * h;
+#pragma unroll
+      for (int pl = 0; pl < NS; ++pl)
+        rv[h][pl] = __ldg(reinterpret_cast<const uint4*>(p.res.base + pl_offset(p.res, pl, ch >> 6, e.m, (ch & 63) >> 3)));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale + n) + j);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + n) + j);
+    o[4 * j] = fmaf(o[4 * j], a.x, b4.x); o[4 * j + 1] = fmaf(o[4 * j + 1], a.y, b4.y);
+    o[4 * j + 2] = fmaf(o[4 * j + 2], a.z, b4.z); o[4 * j + 3] = fmaf(o[4 * j + 3], a.w, b4.w);
+  }
+  if (p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC) {
+    if (!e.staged && !e.valid) return;
+    if (e.has_res) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float f[8];
+        decode8<NS>(rv[h][0], rv[h][NS - 1], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[8 * h + j] += f[j];
+      }
+    }
+    if (p.act == SGTA_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = o[8 * h + j];
+      const int ch = n + 8 * h;
+      if (e.staged) {
+        uint4 e0, e1;
+        encode8<NS>(f, e0, e1);
+        if (!e.valid) { e0 = make_uint4(0, 0, 0, 0); e1 = e0; }
+        const uint32_t a = e.srow + ((((uint32_t)(ch & 63) >> 3) ^ e.sxor) << 4);
+        sts128(a, e0);
+        if (NS == 2) sts128(a + 16384u, e1);
+      } else if (p.epi == SGTA_EPI_PL) pl_store8<NS>(p.y, ch >> 6, e.m, (ch & 63) >> 3, f);
+      else sc_store8<NS>(p.y, e.m, ch, f);
+    }
+  } else if (p.epi == SGTA_EPI_F32ROWS) {
+    if (!e.inP) return;
+    float4* dst = reinterpret_cast<float4*>(p.yf + (size_t)e.m * p.ldyf + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  } else {   // SGTA_EPI_NCHW: fp32 [B, n_valid, Ho, Wo]
+    if (!e.valid) return;
+    const size_t hw = (size_t)p.Ho * p.Wo;
+    float* dst = p.yf + ((size_t)e.b * p.n_valid + n) * hw + (size_t)(e.py - 1) * p.Wo + (e.px - 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (n + j < p.n_valid) {
+        float v = o[j];
+        if (p.act == SGTA_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (p.act == SGTA_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+        dst[(size_t)j * hw] = v;
+      }
+    }
+  }
+}
+
+template <int NS>
+__device__ __forceinline__ void epilogue_group(const ConvP& p, const EpiRow& e, uint32_t tacc, int c0, int n) {
+  float o[16];
+  epi_read<NS>(p, tacc, c0, o);
+  epi_finish<NS>(p, e, n, o);
+}
+
+// NH epilogue warps per lane quadrant; `half` in [0, NH) is this warp's share
+template <int NS, int NH>
+__device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row, uint32_t stage_s,
+                                              int half, uint64_t* release) {
   const int NT = p.NT;
-  const int m = m0 + row;
-  int px, py, b;
-  decode_row(p, m, px, py, b);
-  const bool inP = m < p.P;
-  const bool valid = inP && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
-  const int R = p.acc_r;
+  EpiRow e;
+  e.m = m0 + row;
+  decode_row(p, e.m, e.px, e.py, e.b);
+  e.inP = e.m < p.P;
+  e.valid = e.inP && e.px >= 1 && e.px <= p.Wo && e.py >= 1 && e.py <= p.Ho;
   if (p.epi == SGTA_EPI_STEM) {
     // N = 32: out[c] = relu(bn_a(acc[c])) + relu(bn_b(acc[16+c])), c < 16   (dla.py:325-331)
+    if (half != 0) return;
+    const int R = p.acc_r;
     float fa[16], fb[16];
     read_acc16<NS>(tacc, NT, R, 0, fa);
     read_acc16<NS>(tacc, NT, R, 16, fb);
-    if (valid) {
+    if (e.valid) {
       float o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -190,74 +333,56 @@ __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int
       float lo8[8], hi8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { lo8[j] = o[j]; hi8[j] = o[8 + j]; }
-      sc_store8<NS>(p.y, m, 0, lo8);
-      sc_store8<NS>(p.y, m, 8, hi8);
+      sc_store8<NS>(p.y, e.m, 0, lo8);
+      sc_store8<NS>(p.y, e.m, 8, hi8);
     }
     return;
   }
+  const bool pl_like = p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC;
+  e.has_res = pl_like && e.valid && p.res.base != nullptr;
+  e.staged = stage_s != 0 && p.epi == SGTA_EPI_PL && m0 + TM <= p.P;
+  e.srow = stage_s + (uint32_t)row * 128u;
+  e.sxor = (uint32_t)((p.y.guard + e.m) & 7);
+  if (NS == 2 && NH == 1 && release != nullptr && NT == 128 && !e.staged) {
+    // single accumulator stage (fp32 mode, 128-wide tile): drain the whole row into registers, hand
+    // TMEM back to the MMA warp, THEN do the math and the stores -- they overlap the next tile's MMAs
+    float o[8][16];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      __syncwarp();
+      read_acc16<NS>(tacc, NT, p.acc_r, g * 16, o[g]);       // one 16-register buffer: o[8][16] is the budget
+    }
+    tc_fence_before();
+    __syncwarp();
+    if ((row & 31) == 0) mbar_arrive(release);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) epi_finish<NS>(p, e, n0 + g * 16, o[g]);
+    return;
+  }
+  const int G = (NT < 64 ? NT : 64) >> 4;              // 16-column groups per chunk: 1, 2 or 4
+  const bool leader = row == 0 && half == 0;
   for (int c0 = 0; c0 < NT; c0 += 16) {
     __syncwarp();                      // tcgen05.ld is warp-collective: reconverge after the stores
     const int n = n0 + c0;
-    float o[16];
-    read_acc16<NS>(tacc, NT, R, c0, o);
+    if (e.staged && (c0 & 63) == 0) {  // staging tile free again: the previous chunk's bulk store has read it
+      if (leader) bulk_wait_read0();
+      epi_bar<NH>();
+    }
+    const int gi = (c0 >> 4) & (G - 1);
+    const bool mine = NH == 1 || (G == 1 ? half == 0 : (gi * NH) / G == half);
+    if (mine) epilogue_group<NS>(p, e, tacc, c0, n);
+    if (e.staged && (c0 & 63) == 48) {
+      fence_async_smem();
+      epi_bar<NH>();
+      if (leader) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = fmaf(o[j], __ldg(p.scale + n + j), __ldg(p.shift + n + j));
-    if (p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC) {
-      if (!valid) continue;
-      if (p.res.base) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float f[8];
-          const int ch = n + 8 * h;
-          pl_load8<NS>(p.res, ch >> 6, m, (ch & 63) >> 3, f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[8 * h + j] += f[j];
-        }
-      }
-      if (p.act == SGTA_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = o[8 * h + j];
-        const int ch = n + 8 * h;
-        if (p.epi == SGTA_EPI_PL) pl_store8<NS>(p.y, ch >> 6, m, (ch & 63) >> 3, f);
-        else sc_store8<NS>(p.y, m, ch, f);
-      }
-    } else if (p.epi == SGTA_EPI_F32ROWS) {
-      if (!inP) continue;
-      float4* dst = reinterpret_cast<float4*>(p.yf + (size_t)m * p.ldyf + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-    } else {   // SGTA_EPI_NCHW: fp32 [B, n_valid, Ho, Wo]
-      if (!valid) continue;
-      const size_t hw = (size_t)p.Ho * p.Wo;
-      float* dst = p.yf + ((size_t)b * p.n_valid + n) * hw + (size_t)(py - 1) * p.Wo + (px - 1);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (n + j < p.n_valid) {
-          float v = o[j];
-          if (p.act == SGTA_ACT_RELU) v = fmaxf(v, 0.f);
-          else if (p.act == SGTA_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
-          dst[(size_t)j * hw] = v;
-        }
+        for (int pl = 0; pl < NS; ++pl)
+          bulk_s2g(p.y.base + ((((size_t)pl * p.y.nchunks + p.y.chunk0 + (n >> 6)) * p.y.rows + p.y.guard + m0) << 7),
+                   stage_s + (uint32_t)pl * 16384u, 16384u);
+        bulk_commit();
       }
     }
   }
-}
-
-// explicit shared-memory accesses (pointers derived from the dynamic smem base otherwise compile to
-// generic LD / ST)
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ unsigned char* align1024(unsigned char* p) {
@@ -280,8 +405,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   const int NT = p.NT;
   const uint32_t a_plane = (uint32_t)p.a_rows * 128u, a_stage = a_plane * NS;
   const uint32_t b_plane = (uint32_t)NT * 128u, b_stage = b_plane * NS;
-  unsigned char* sA = smem;
-  unsigned char* sB = smem + (size_t)p.SA * a_stage;
+  unsigned char* sA = smem + p.stg_bytes;
+  unsigned char* sB = sA + (size_t)p.SA * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.SB * b_stage);
   uint64_t *a_full = bars, *a_empty = bars + 8, *b_full = bars + 16, *b_empty = bars + 24;
   uint64_t *acc_full = bars + 32, *acc_empty = bars + 34;
@@ -290,7 +415,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], NS); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * S_EPI_NH); }
     fence_mbar_init();
   }
   if (warp == S_TMA_WARPS) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
@@ -404,19 +529,23 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - (S_TMA_WARPS + 1)) >> 2;
+    // the tile releases its accumulators itself, right after reading them (see epilogue_tile)
+    const bool early = NS == 2 && S_EPI_NH == 1 && p.acc_stages == 1 && NT == 128 && p.stg_bytes == 0 && p.epi != SGTA_EPI_STEM;
     uint32_t as = 0, accph = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
       mbar_wait_backoff(&acc_full[as], accph);
       tc_fence_after();
       if (!(p.dbg & 4))
-        epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+        epilogue_tile<NS, S_EPI_NH>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
+                                    p.stg_bytes ? smem_u32(smem) : 0u, half, early ? &acc_empty[as] : nullptr);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0 && !(early && !(p.dbg & 4))) mbar_arrive(&acc_empty[as]);
       if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
     }
+    if (q == 0 && half == 0 && lane == 0) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -433,7 +562,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
   const uint32_t b_plane = (uint32_t)NT * 128u, b_bytes = b_plane * NS;
   // ring stage = [A | B]; with resident weights the ring holds A only and all B blocks sit behind it
   const uint32_t stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
-  unsigned char* sBres = smem + (size_t)p.SA * stage_bytes;
+  unsigned char* ring = smem + p.stg_bytes;            // [epilogue store staging | operand ring | ...]
+  unsigned char* sBres = ring + (size_t)p.SA * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBres + (p.b_resident ? (size_t)p.nkb * b_bytes : 0));
   uint64_t *full = bars, *empty = bars + 8, *acc_full = bars + 16, *acc_empty = bars + 18;
   uint64_t* b_ready = bars + 21;
@@ -465,7 +595,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
     uint32_t pph = 1;
     auto wait_stage = [&]() -> unsigned char* {
       mbar_wait(&empty[pst], pph);
-      return smem + (size_t)pst * stage_bytes;
+      return ring + (size_t)pst * stage_bytes;
     };
     auto publish = [&]() {
       fence_async_smem();
@@ -718,7 +848,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
             const int blk = PROD == PROD_SMALLC ? kb : tap * p.KC + kc;
             mbar_wait(&empty[s], ph);
             mbar_arrive_expect_tx(&full[s], b_bytes);
-            bulk_g2s(smem + (size_t)s * stage_bytes + a_bytes, wt + (size_t)blk * b_bytes, b_bytes, &full[s]);
+            bulk_g2s(ring + (size_t)s * stage_bytes + a_bytes, wt + (size_t)blk * b_bytes, b_bytes, &full[s]);
             if (++s == p.SA) { s = 0; ph ^= 1u; }
             if (++tap == 9) { tap = 0; ++kc; }
           }
@@ -731,7 +861,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
     constexpr int R = AccR<NS>::value;
     int s = 0;
     uint32_t ph = 0, as = 0, accph = 1;
-    const uint32_t smem0 = smem_u32(smem), bres0 = smem_u32(sBres);
+    const uint32_t smem0 = smem_u32(ring), bres0 = smem_u32(sBres);
     if (p.b_resident) mbar_wait(b_ready, 0);
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       mbar_wait(&acc_empty[as], accph);
@@ -768,12 +898,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
       mbar_wait_backoff(&acc_full[as], accph);
       tc_fence_after();
       if (!(p.dbg & 4))
-        epilogue_tile<NS>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane);
+        epilogue_tile<NS, 1>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
+                             p.stg_bytes ? smem_u32(smem) : 0u, 0, nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
     }
+    if (q == 0 && lane == 0) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -806,7 +938,7 @@ __global__ void pack_weight_planes_kernel(const float* __restrict__ wm, unsigned
 
 static int pick_ntile(int Cout, int NS) {
   if (Cout < 16 || Cout % 16) return -1;
-  const int cap = NS == 2 ? 128 : 256;
+  const int cap = (g_dbg & 64) ? 64 : NS == 2 ? 128 : 256;
   int nt = Cout;
   if (nt > cap) {
     nt = cap;
@@ -830,11 +962,21 @@ static void plan_acc(ConvP& p, int NS, bool short_k = false) {
 template <int NS>
 static int launch_shift(ConvP& p, cudaStream_t st) {
   const int a_stage = p.a_rows * 128 * NS, b_stage = p.NT * 128 * NS;
-  const int fixed = 1024 + 512;
-  int SB = 4, SA = 3;
-  while (SB > 2 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SB;
-  while (SA > 1 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SA;
-  if (SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) { set_error("conv_shift: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
+  // a 3x3 band consumes THREE B slots before it releases any (SB < 3 deadlocks); one more slot is the
+  // whole weight prefetch, so the epilogue's store staging is only taken when SB >= 4 still fits
+  const int min_sb = p.taps == 9 ? 3 : 2;
+  int fixed = 0, SA = 0, SB = 0;
+  // (fp32 mode: measured no gain -- the hi/lo tile needs 32 KB that the weight ring uses better)
+  for (int with_stg = (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 1 : 0; with_stg >= 0; --with_stg) {
+    p.stg_bytes = with_stg ? 16384 * NS : 0;
+    fixed = 1024 + 512 + p.stg_bytes;
+    SB = 4; SA = 3;
+    while (SB > min_sb && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SB;
+    while (SA > 1 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SA;
+    const bool fits = SA * a_stage + SB * b_stage + fixed <= SMEM_LIMIT;
+    if (fits && (!with_stg || (SB >= min_sb + 1 && SA >= 2))) break;
+    if (!with_stg) { set_error("conv_shift: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
+  }
   // spend what is left on deeper rings
   while (SA < 6 && (SA + 1) * a_stage + SB * b_stage + fixed <= SMEM_LIMIT && SA <= SB) ++SA;
   while (SB < 8 && SA * a_stage + (SB + 1) * b_stage + fixed <= SMEM_LIMIT) ++SB;
@@ -857,7 +999,8 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
 template <int PROD, int NS>
 static int launch_gather(ConvP& p, cudaStream_t st) {
   const int a_bytes = TM * 128 * NS, b_bytes = p.NT * 128 * NS;
-  const int fixed = 1024 + 512 + (PROD == PROD_DCN ? 9 * TM * 32 : 0);
+  p.stg_bytes = NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8) ? 16384 * NS : 0;
+  const int fixed = 1024 + 512 + p.stg_bytes + (PROD == PROD_DCN ? 9 * TM * 32 : 0);
   // weights resident in shared memory when one CTA sees a single N tile and they leave room for
   // >= 2 A stages: no per-K-block weight copy (a single thread's bulk copies serialise, ~530 clk each)
   p.b_resident = p.n_tiles == 1 && fixed + p.nkb * b_bytes + 2 * a_bytes <= SMEM_LIMIT;
