@@ -104,6 +104,182 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward, batch-looping variant (the one the engine runs).  pos_embed[h, rows, :] is shared by every
+// sample of the batch: re-reading it per sample costs B x 44.8 MB of L2 traffic per launch at level 0
+// (1.4 GB at B = 32, as long as the whole old kernel).  Here a CTA owns (32 query rows, head) and
+// keeps that pos block in shared memory (151 KB at n = 1183) while it loops over its samples; K / V
+// of the next sample are prefetched into registers during the current sample's math.  A warp
+// processes RW query rows per pass so each K / V shared-memory read feeds RW rows, the running max is
+// only rescaled when some key of the pass raises it, and exp2 is the bare MUFU instruction.
+template <int D> struct RowsPerPass { static constexpr int value = D == 4 ? 4 : D == 8 ? 2 : 1; };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr float LAZY = 8.f;
+constexpr int ATB_WARPS = 16;          // batched kernel: 4 warps per SM sub-partition hide the exp2 -> fma chains
+constexpr int ATB_THREADS = ATB_WARPS * 32;
+
+template <int D>
+__global__ void __launch_bounds__(ATB_THREADS, 1)
+attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                        const float* __restrict__ pos, float* __restrict__ out, int B, int heads, int nq, int nk,
+                        int nk_pad, int b_per_cta, float inv_scale) {
+  constexpr int S = KPad<D>::stride;
+  constexpr int V4 = D / 4;
+  constexpr int RW = RowsPerPass<D>::value;
+  constexpr int GROUPS = ATT_ROWS / RW;                               // row groups per CTA
+  constexpr int KS = ATB_WARPS / GROUPS >= 1 ? ATB_WARPS / GROUPS : 1;   // warps that split the keys of one group
+  constexpr int WG = ATB_WARPS / KS;                                  // row groups processed concurrently
+  constexpr int PF = 5;                       // float4 pairs of K/V prefetch per thread (covers nk*V4 <= 2560)
+  extern __shared__ __align__(16) float att_smem[];
+  float* Ks = att_smem;
+  float* Vs = Ks + (size_t)nk * S;
+  float* Part = Vs + (size_t)nk * S;         // [KS][ATT_ROWS][D + 2] partial (acc, m, l) per key split
+  float* Ps = Part + KS * ATT_ROWS * (D + 2);   // [ATT_ROWS][nk_pad]
+  const int h = blockIdx.y;
+  const int HD = heads * D;
+  const int row0 = blockIdx.x * ATT_ROWS;
+  const int b_begin = blockIdx.z * b_per_cta, b_end = min(B, b_begin + b_per_cta);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = nk * V4;
+  const int grp = warp % WG, ks = warp / WG;
+
+  if (pos) {
+    for (int r = warp; r < ATT_ROWS; r += ATB_WARPS) {
+      const int i = row0 + r;
+      if (i >= nq) break;
+      const float* prow = pos + ((long long)h * nq + i) * nk;
+      for (int j = lane; j < nk; j += 32) Ps[r * nk_pad + j] = __ldg(prow + j) * LOG2E;
+    }
+  }
+  float4 kreg[PF], vreg[PF];
+  auto prefetch = [&](int b) {
+    const float* kb = k + (long long)b * nk * HD + h * D;
+    const float* vb = v + (long long)b * nk * HD + h * D;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int e = tid + u * ATB_THREADS;
+      if (e < nvec) {
+        const int j = e / V4, c = (e % V4) * 4;
+        kreg[u] = __ldg(reinterpret_cast<const float4*>(kb + (long long)j * HD + c));
+        vreg[u] = __ldg(reinterpret_cast<const float4*>(vb + (long long)j * HD + c));
+      }
+    }
+  };
+  if (b_begin < b_end) prefetch(b_begin);
+  const float sc = inv_scale * LOG2E;
+
+  for (int b = b_begin; b < b_end; ++b) {
+    __syncthreads();                          // previous sample: K / V consumed, partials merged
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int e = tid + u * ATB_THREADS;
+      if (e < nvec) {
+        const int j = e / V4, c = (e % V4) * 4;
+        *reinterpret_cast<float4*>(Ks + j * S + c) = kreg[u];
+        *reinterpret_cast<float4*>(Vs + j * S + c) = vreg[u];
+      }
+    }
+    __syncthreads();
+    if (b + 1 < b_end) prefetch(b + 1);
+
+    for (int g = grp; g < GROUPS; g += WG) {
+      const int r = g * RW;
+      float qr[RW][D], m[RW], l[RW], acc[RW][D];
+#pragma unroll
+      for (int w = 0; w < RW; ++w) {
+        const int i = min(row0 + r + w, nq - 1);      // rows past the end recompute the last row (not stored)
+        load_row<D>(qr[w], q + ((long long)b * nq + i) * HD + h * D);
+        m[w] = -INFINITY; l[w] = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { qr[w][c] *= sc; acc[w][c] = 0.f; }
+      }
+      const float* prow = Ps + (size_t)r * nk_pad;
+      // lazy rescale: a row's reference point mt - LAZY only moves when a score exceeds it by 2^LAZY;
+      // exponentials stay <= 2^LAZY (exact in the final ratio).  The rescale is behind a WARP-UNIFORM
+      // vote so it stays a real, rarely taken branch (a per-lane `if` is if-converted by the compiler
+      // and its ex2 + D+1 multiplies then run on every key)
+      float mt[RW];
+#pragma unroll
+      for (int w = 0; w < RW; ++w) mt[w] = -INFINITY;
+#pragma unroll 2
+      for (int jb = ks * 32; jb < nk; jb += 32 * KS) {       // warp-uniform trip count (the vote below)
+        const bool live = jb + lane < nk;
+        const int j = live ? jb + lane : nk - 1;
+        float kr[D], vr[D], sv[RW];
+        load_row<D>(kr, Ks + j * S);
+        load_row<D>(vr, Vs + j * S);
+        bool up = false;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+          sv[w] = pos ? prow[w * nk_pad + j] : 0.f;
+#pragma unroll
+          for (int c = 0; c < D; ++c) sv[w] = fmaf(qr[w][c], kr[c], sv[w]);
+          up |= live && sv[w] > mt[w];
+        }
+        if (__any_sync(0xffffffffu, up)) {
+          // the reference point is shared by the warp (the max over all 32 keys of this step), so it
+          // converges after a few steps and the final merge needs no per-lane rescale
+#pragma unroll
+          for (int w = 0; w < RW; ++w) {
+            if (__any_sync(0xffffffffu, live && sv[w] > mt[w])) {
+              const float nm = fmaxf(warp_max(live ? sv[w] : -INFINITY), m[w]);
+              const float corr = (m[w] == -INFINITY) ? 0.f : ex2_approx(m[w] - nm);
+              l[w] *= corr;
+#pragma unroll
+              for (int c = 0; c < D; ++c) acc[w][c] *= corr;
+              m[w] = nm;
+              mt[w] = nm + LAZY;
+            }
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+          const float pw = live ? ex2_approx(sv[w] - m[w]) : 0.f;
+          l[w] += pw;
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc[w][c] = fmaf(pw, vr[c], acc[w][c]);
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < RW; ++w) {
+        const float M = m[w];                                    // warp-uniform
+        const float L = warp_sum(l[w]);
+        float* pr = Part + ((size_t)ks * ATT_ROWS + r + w) * (D + 2);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const float a = warp_sum(acc[w][c]);
+          if (lane == c) pr[c] = a;
+        }
+        if (lane == 0) { pr[D] = M; pr[D + 1] = L; }
+      }
+    }
+    __syncthreads();
+    // merge the key splits: one thread per (row, channel)
+    for (int e = tid; e < ATT_ROWS * D; e += ATB_THREADS) {
+      const int r = e / D, c = e % D;
+      if (row0 + r >= nq) continue;
+      float M = -INFINITY;
+#pragma unroll
+      for (int s2 = 0; s2 < KS; ++s2) M = fmaxf(M, Part[((size_t)s2 * ATT_ROWS + r) * (D + 2) + D]);
+      float L = 0.f, a = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < KS; ++s2) {
+        const float* pr = Part + ((size_t)s2 * ATT_ROWS + r) * (D + 2);
+        const float f = pr[D] == -INFINITY ? 0.f : ex2_approx(pr[D] - M);
+        L = fmaf(pr[D + 1], f, L);
+        a = fmaf(pr[c], f, a);
+      }
+      out[((long long)b * nq + row0 + r) * HD + h * D + c] = a / L;
+    }
+  }
+}
+
 // Backward of the same core.  One warp per query row; recomputes the softmax statistics,
 // then ds_j = p_j (dp_j - delta) with delta = gout_i . out_i.
 //   gq_i = inv_scale * sum_j ds_j k_j          (registers + warp reduce)
@@ -187,6 +363,29 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
 template <int D>
 static int launch_fwd(const float* q, const float* k, const float* v, const float* pos, float* out,
                       int B, int heads, int nq, int nk, float inv_scale, cudaStream_t st) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  // batch-looping kernel for LARGE pos_embed blocks (level 0: 44.8 MB re-read per sample otherwise):
+  // pos block + K/V of one sample in shared memory; the prefetch registers cover nk*D/4 <= 2560
+  constexpr int RWv = RowsPerPass<D>::value;
+  constexpr int KSv = ATB_WARPS / (ATT_ROWS / RWv) >= 1 ? ATB_WARPS / (ATT_ROWS / RWv) : 1;
+  const int nk_pad = nk + ((33 - (nk & 31)) & 31);           // row stride = 1 mod 32: the RW rows of a pass hit distinct banks
+  const size_t smem_b = sizeof(float) * (2 * (size_t)nk * KPad<D>::stride + (size_t)KSv * ATT_ROWS * (D + 2) +
+                                         (size_t)ATT_ROWS * nk_pad);
+  const bool big_pos = pos != nullptr && (size_t)heads * nq * nk * sizeof(float) > (16u << 20) && B >= 4;
+  if (big_pos && smem_b <= 226 * 1024 && (long long)nk * (D / 4) <= 2560) {
+    const int blocks_xy = cdiv(nq, ATT_ROWS) * heads;
+    int zchunks = cdiv(2 * sms, blocks_xy);                    // >= 2 CTAs per SM worth of parallelism when B allows
+    if (zchunks > B) zchunks = B;
+    if (zchunks < 1) zchunks = 1;
+    const int b_per_cta = cdiv(B, zchunks);
+    zchunks = cdiv(B, b_per_cta);
+    cudaFuncSetAttribute(attn_fwd_batched_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    dim3 grid(cdiv(nq, ATT_ROWS), heads, zchunks);
+    attn_fwd_batched_kernel<D><<<grid, ATB_THREADS, smem_b, st>>>(q, k, v, pos, out, B, heads, nq, nk, nk_pad,
+                                                                b_per_cta, inv_scale);
+    return check_launch("attn_fwd_batched_kernel");
+  }
   size_t smem = sizeof(float) * 2 * (size_t)nk * KPad<D>::stride;
   SGTA_REQUIRE(smem <= 220 * 1024, "sgta_attn_forward: nk=%d too large for shared memory", nk);
   if (smem > 48 * 1024)

@@ -91,7 +91,7 @@ def test_dcn_backward_vs_autograd():
 
 
 # ------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("n,d,B", [(1183, 4, 2), (343, 8, 2), (63, 16, 3), (7, 32, 1)])
+@pytest.mark.parametrize("n,d,B", [(1183, 4, 2), (1183, 4, 5), (343, 8, 2), (63, 16, 3), (7, 32, 1)])
 def test_attention_core_vs_torch(n, d, B):
     from sgtapose_b200.fusion import attention_core
     heads = 8
