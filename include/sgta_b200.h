@@ -277,6 +277,20 @@ int sgta_nms3x3(const void* hm, void* out, int B, int C, int h, int w, void* str
 int sgta_soft_argmax(const void* hm, void* out, int B, int C, int h, int w, float beta,
                      float size_mult, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Structure-prior maps: replaces the host rendering + 4 H2D copies per clip
+ * and frame of lib/sgta_detector.py:528-540 (sgtapose/utilities.py:1045-1057 get_prev_hm_wo_noise,
+ * :1085-1098 get_prev_hm_wo_noise_cls, :800-824 draw_umich_gaussian, :846-853 gaussian2D).
+ *   centres_in  [B,K,2] float64 DEVICE: keypoint centres (x,y) in network-INPUT pixels, already
+ *               affine-transformed and clipped like utilities.py:943-972 (points outside the raw
+ *               image = (0,0)); rendered max-blended into hm [B,1,H,W] fp32 (NULL = skip)
+ *   centres_out [B,K,2] float64 DEVICE: the same in network-OUTPUT pixels; rendered one map per
+ *               keypoint into hm_cls [B,K,h,w] fp32 (NULL = skip)
+ *   gauss9x9    HOST pointer, 81 floats: gaussian2D((9,9), sigma=2) rounded to fp32
+ * Every pixel of both maps is written (zeros included).  W and w must be multiples of 4. */
+int sgta_render_priors(const void* centres_in, const void* centres_out, void* hm, void* hm_cls,
+                       const float* gauss9x9, int B, int K, int H, int W, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

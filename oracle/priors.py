@@ -31,8 +31,7 @@ def gaussian_table(radius=RADIUS, sigma=SIGMA):
 
 def get_affine_transform(center, scale, output_size):
     """utilities.py:889-925 for rot = 0, shift = 0, inv = 0.  The three point pairs are
-    (c, c + (0, -s/2), third point); for rot = 0 the solution is closed form, computed here
-    in float32 inputs / float64 solve like cv2.getAffineTransform."""
+    (c, c + (0, -s/2), third point), float32, handed to cv2.getAffineTransform like the reference."""
     if not isinstance(scale, (np.ndarray, list)):
         scale = np.array([scale, scale], dtype=np.float32)
     src_w = scale[0]
@@ -48,9 +47,8 @@ def get_affine_transform(center, scale, output_size):
     for a in (src, dst):
         d = a[0] - a[1]
         a[2] = a[1] + np.array([-d[1], d[0]], np.float32)
-    # solve [x y 1] M^T = dst for the 2x3 matrix (what cv2.getAffineTransform does, in double)
-    A = np.concatenate([src.astype(np.float64), np.ones((3, 1))], 1)
-    return np.linalg.solve(A, dst.astype(np.float64)).T
+    import cv2                      # the reference calls cv2.getAffineTransform (utilities.py:919-922): same solver
+    return cv2.getAffineTransform(np.float32(src), np.float32(dst))
 
 
 def affine_transform_and_clip(pts, t, width, height, raw_width, raw_height):

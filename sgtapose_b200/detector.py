@@ -1,0 +1,187 @@
+"""Lock-step clip runner: the per-frame loop of the reference detector for B clips at once.
+
+Mirrors `SGTADetector.run` / `process` / `post_process` / `_get_final_kps`
+(sgtapose/lib/sgta_detector.py:117-236, :881-927, :929-942, :608-651) and the PnP front-end
+`_get_further_dt_pnp_inputs_real` -> `geometric_vision.is_pnp` -> `solve_pnp`
+(sgta_detector.py:501-547, sgtapose/geometric_vision.py:43-116, :283-310) with these differences,
+all about WHERE things run, none about what is computed:
+
+  * B independent clips advance one frame per `step` (clips are independent, frames serial:
+    SURVEY.md 3.1); the network + decode run once for the whole batch (engine.InferenceEngine);
+  * the four prior maps are rendered on the device from 2 x 7 centres per clip (priors.py)
+    instead of on the host followed by four uploads; the previous frame's image stays on the
+    device (the reference keeps `self.pre_images` there too, sgta_detector.py:204);
+  * decoded detections come back in ONE device->host copy per step ([B,7] scores + [B,7,2]
+    centres) instead of ~7 per clip;
+  * the per-clip PnP (cv2, host, as north_star wants) runs on a thread pool -- cv2 releases the GIL.
+
+Keypoint 3-D positions w.r.t. the camera for the previous / current frame are inputs (the
+reference reads them from the frame JSONs, sgta_detector.py:511-517).  Image pre-processing
+(cv2 warpAffine + normalise, :368-399) is outside this module: `step` takes network-input images.
+"""
+import concurrent.futures as cf
+import time
+
+import numpy as np
+import torch
+
+from . import priors as PR
+
+MISSING = -999.999 * 4          # sgta_detector.py:613, :521
+DEFAULT_K = np.array([[502.30, 0.0, 319.75], [0.0, 502.30, 179.75], [0.0, 0.0, 1.0]])   # sgta_detector.py:83
+
+
+def _rotation_from_rvec(rvec):
+    """geometric_vision.py:15-25 convert_rvec_to_quaternion (pyrr Quaternion.from_axis_rotation, normalised)
+    followed by `.matrix33` (:291).  pyrr is an un-pinned, absent dependency: restated from its published
+    formulas (pyrr 0.10.3 quaternion.create_from_axis_rotation / matrix33.create_from_quaternion)."""
+    theta = np.sqrt(rvec[0] * rvec[0] + rvec[1] * rvec[1] + rvec[2] * rvec[2])
+    axis = np.array([rvec[0] / theta, rvec[1] / theta, rvec[2] / theta], dtype=np.float64)
+    half = theta * 0.5
+    s = np.sin(half)
+    qx, qy, qz, qw = axis[0] * s, axis[1] * s, axis[2] * s, np.cos(half)
+    n = np.sqrt(qx * qx + qy * qy + qz * qz + qw * qw)
+    qx, qy, qz, qw = qx / n, qy / n, qz / n, qw / n
+    sqw, sqx, sqy, sqz = qw * qw, qx * qx, qy * qy, qz * qz
+    inv = 1.0 / (sqx + sqy + sqz + sqw)
+    return np.array([
+        [(sqx - sqy - sqz + sqw) * inv, 2.0 * (qx * qy - qz * qw) * inv, 2.0 * (qx * qz + qy * qw) * inv],
+        [2.0 * (qx * qy + qz * qw) * inv, (-sqx + sqy - sqz + sqw) * inv, 2.0 * (qy * qz - qx * qw) * inv],
+        [2.0 * (qx * qz - qy * qw) * inv, 2.0 * (qy * qz + qx * qw) * inv, (-sqx - sqy + sqz + sqw) * inv]])
+
+
+def solve_pnp(canonical_points, projections, camera_K):
+    """geometric_vision.py:43-116: cv2 EPnP, then ITERATIVE refinement from that guess.
+    -> (ok, translation [3], rotation [3,3])"""
+    import cv2
+    pts = np.asarray(canonical_points, np.float64)
+    prj = np.asarray(projections, np.float64)
+    if len(pts) == 0 or len(pts) != len(prj):
+        return False, None, None
+    try:
+        ok, rvec, tvec = cv2.solvePnP(pts.reshape(-1, 1, 3), prj.reshape(-1, 1, 2), camera_K, np.array([]),
+                                      flags=cv2.SOLVEPNP_EPNP)
+        ok, rvec, tvec = cv2.solvePnP(pts.reshape(-1, 1, 3), prj.reshape(-1, 1, 2), camera_K, np.array([]),
+                                      flags=cv2.SOLVEPNP_ITERATIVE, useExtrinsicGuess=True, rvec=rvec, tvec=tvec)
+        return bool(ok), tvec[:, 0], _rotation_from_rvec(rvec[:, 0])
+    except Exception:                       # the reference swallows solver failures the same way (:111-114)
+        return False, None, None
+
+
+def is_pnp(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K):
+    """geometric_vision.py:283-310: pose of the previous frame's detections, applied to the current
+    frame's keypoint positions and projected.  -> (prev_kp_projs, next_kp_projs_est)"""
+    ok, t, R = solve_pnp(prev_pos, prev_projs, camera_K)
+    if not ok:
+        return prev_projs_all, prev_projs_all
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, -1] = t
+    hom = np.hstack((next_pos, np.ones((next_pos.shape[0], 1))))
+    aligned = np.transpose(np.matmul(T, np.transpose(hom)))[:, :3]
+    est = np.transpose(np.matmul(camera_K, np.transpose(aligned)))
+    est[:, 0] /= est[:, 2]
+    est[:, 1] /= est[:, 2]
+    return prev_projs_all, est[:, :2]
+
+
+class LockstepDetector:
+    def __init__(self, engine, opt=None, camera_K=None, raw_size=(640, 360), workers=8):
+        self.eng = engine
+        self.opt = opt if opt is not None else engine.opt
+        self.K = np.array(DEFAULT_K if camera_K is None else camera_K, dtype=np.float64)
+        self.raw_w, self.raw_h = raw_size
+        self.B, self.S = engine.B, engine.S
+        self.q = self.S // int(getattr(self.opt, "down_ratio", 4))
+        self.n_kp = int(getattr(self.opt, "num_classes", 7))
+        self.out_thresh = max(float(getattr(self.opt, "track_thresh", 0.001)), float(getattr(self.opt, "out_thresh", -1)))
+        # fix_res pre-processing geometry (sgta_detector.py:354-357, :375-380)
+        c = np.array([self.raw_w / 2.0, self.raw_h / 2.0], dtype=np.float32)
+        s = max(self.raw_h, self.raw_w) * 1.0
+        self.trans_input = PR.get_affine_transform(c, s, 0, [self.S, self.S])
+        self.trans_output = PR.get_affine_transform(c, s, 0, [self.q, self.q])
+        # post_process: inverse output affine in float32 (post_process.py:102-103)
+        self.trans_inv = PR.get_affine_transform(c, s, 0, (self.q, self.q), inv=1).astype(np.float32)
+        self.pool = cf.ThreadPoolExecutor(max_workers=workers) if workers > 1 else None
+        dev = engine.dev
+        self._c_in = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64).pin_memory()
+        self._c_out = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64).pin_memory()
+        self._d_in = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64, device=dev)
+        self._d_out = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64, device=dev)
+        self._res = torch.zeros(self.B, self.n_kp, 3, dtype=torch.float32).pin_memory()
+        self.reset()
+
+    def reset(self):
+        self.frame = 0
+        self.detected_kps = np.full((self.B, self.n_kp, 2), MISSING)
+        self.timing = {"host_pnp": 0.0, "host_post": 0.0, "steps": 0}
+
+    # ------------------------------------------------------------------ host side of one clip
+    def _clip_centres(self, b, x3d_prev, x3d_next):
+        """sgta_detector.py:501-547 up to the four rendering calls: raw-pixel keypoints of the two
+        prior maps of clip b, or None when nothing was detected (all-zero maps, :523-526)."""
+        kps = self.detected_kps[b]
+        good = np.unique(np.where(kps > MISSING)[0])
+        if len(good) == 0:
+            return None, None
+        return is_pnp(x3d_prev[good], kps[good], x3d_next, kps, self.K)
+
+    def _post(self, scores, cts_wreg):
+        """post_process (:929-942 -> post_process.py:93-117), merge_outputs (:955-961) and _get_final_kps
+        (:608-651) for the whole batch: the best-scoring detection of every class, in raw-image pixels."""
+        B, K = scores.shape
+        ones = np.ones((B * K, 3), np.float32)
+        ones[:, :2] = cts_wreg.reshape(-1, 2)
+        raw = np.dot(self.trans_inv, ones.transpose()).transpose()[:, :2].reshape(B, K, 2)   # image.py:20-26
+        keep = (scores >= self.out_thresh) & (scores > self.out_thresh)
+        out = np.full((B, K, 2), MISSING)
+        out[keep] = raw[keep]
+        return out
+
+    # ------------------------------------------------------------------ one frame of every clip
+    def step(self, images, x3d_prev=None, x3d_next=None):
+        """images [B,3,S,S] fp32 (device or pinned host).  x3d_prev / x3d_next: [B,n_kp,3] keypoint
+        positions w.r.t. the camera in the previous / this frame (ignored at frame 0).
+        Returns {'kps_raw' [B,n_kp,2] float64 (MISSING = not detected), 'scores' [B,n_kp]}."""
+        eng, inp = self.eng, self.eng.inp
+        t0 = time.perf_counter()
+        if self.frame == 0:
+            # _get_additional_inputs (:415-454): all-zero priors, pre_images = images (:157-159)
+            for k in ("pre_hm", "repro_hm", "pre_hm_cls", "repro_hm_cls"):
+                inp[k].zero_()
+            inp["x"].copy_(images, non_blocking=True)
+            inp["pre_img"].copy_(inp["x"])
+        else:
+            inp["pre_img"].copy_(inp["x"])                       # self.pre_images = images (:204)
+            inp["x"].copy_(images, non_blocking=True)
+            jobs = [(b, x3d_prev[b], x3d_next[b]) for b in range(self.B)]
+            res = list(self.pool.map(lambda a: self._clip_centres(*a), jobs)) if self.pool else \
+                [self._clip_centres(*a) for a in jobs]
+            far = np.full((self.n_kp, 2), -1.0)                  # outside the raw image -> (0,0) -> nothing drawn
+            prev = np.stack([far if r[0] is None else r[0] for r in res])
+            nxt = np.stack([far if r[1] is None else r[1] for r in res])
+            for i, pts in enumerate((prev, nxt)):
+                self._c_in[i].copy_(torch.from_numpy(PR.affine_transform_and_clip(
+                    pts, self.trans_input, self.S, self.S, self.raw_w, self.raw_h)))
+                self._c_out[i].copy_(torch.from_numpy(PR.affine_transform_and_clip(
+                    pts, self.trans_output, self.q, self.q, self.raw_w, self.raw_h)))
+            self._d_in.copy_(self._c_in, non_blocking=True)
+            self._d_out.copy_(self._c_out, non_blocking=True)
+            PR.render_priors(self._d_in[0], self._d_out[0], self.S, self.q, hm=inp["pre_hm"], hm_cls=inp["pre_hm_cls"])
+            PR.render_priors(self._d_in[1], self._d_out[1], self.S, self.q, hm=inp["repro_hm"], hm_cls=inp["repro_hm_cls"])
+        t1 = time.perf_counter()
+        dets = eng.infer()
+        packed = torch.cat([dets["scores"].view(self.B, self.n_kp, 1),
+                            dets["cts_wreg"].view(self.B, self.n_kp, 2)], dim=2)
+        self._res.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        t2 = time.perf_counter()
+        r = self._res.numpy()
+        scores = r[:, :, 0].copy()
+        self.detected_kps = self._post(scores, r[:, :, 1:3])
+        t3 = time.perf_counter()
+        self.timing["host_pnp"] += t1 - t0
+        self.timing["host_post"] += t3 - t2
+        self.timing["steps"] += 1
+        self.frame += 1
+        return {"kps_raw": self.detected_kps.copy(), "scores": scores}

@@ -322,6 +322,11 @@ class InferenceEngine:
         for k, t in (("x", x), ("pre_img", pre_img), ("pre_hm", pre_hm), ("repro_hm", repro_hm),
                      ("pre_hm_cls", pre_hm_cls), ("repro_hm_cls", repro_hm_cls)):
             self.inp[k].copy_(t, non_blocking=True)
+        return self.forward_static()
+
+    def forward_static(self):
+        """Run the plan on whatever the static input buffers `self.inp` hold (the lock-step clip runner
+        renders the prior maps straight into them, sgtapose_b200/detector.py)."""
         with torch.no_grad():
             if not self._use_graph:
                 self._run()
@@ -339,8 +344,9 @@ class InferenceEngine:
     __call__ = forward
 
     def infer(self, *inputs):
-        """forward -> sigmoid -> live decode, like SGTADetector.process (sgta_detector.py:881-927)."""
-        out = dict(self.forward(*inputs)[0])
+        """forward -> sigmoid -> live decode, like SGTADetector.process (sgta_detector.py:881-927).
+        Without arguments: on the static input buffers."""
+        out = dict((self.forward(*inputs) if inputs else self.forward_static())[0])
         if not self.fuse_sigmoid:
             out["hm"] = torch.sigmoid(out["hm"])
         return decode.dream_generic_decode(out, K=out["hm"].shape[1], opt=self.opt)

@@ -1,0 +1,89 @@
+"""Lock-step clip runner (sgtapose_b200/detector.py) vs the per-clip restatement of the reference's
+host steps (oracle/detector.py) and the oracle's decode -- GPU tests."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode as odec
+from oracle import detector as odet
+from tests import _cases as C
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+S, B = 128, 3
+
+
+def _scene(rng, B, frame):
+    """7 Panda-like keypoints in front of the camera, drifting a little per frame: [B,7,3]."""
+    base = rng.uniform([-0.35, -0.2, 1.2], [0.35, 0.2, 1.8], size=(B, 7, 3))
+    return base + 0.004 * frame
+
+
+@pytest.fixture(scope="module")
+def det():
+    from sgtapose_b200 import config, detector, engine, networks, synth
+    m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=C.GOLDEN_SEED)
+    eng = engine.InferenceEngine(sd, config.default_opt(), batch=B, size=S, mode="fp32", device=DEV, fuse_sigmoid=True)
+    return detector.LockstepDetector(eng, workers=4)
+
+
+def test_post_process_matches_reference_loops(det):
+    rng = np.random.default_rng(1)
+    scores = rng.uniform(-1, 1, size=(B, 7)).astype(np.float32)
+    scores[0, 2] = -1.0
+    scores[1] = 0.0005                                   # below out_thresh = 0.001
+    cts = rng.uniform(0, S // 4, size=(B, 7, 2)).astype(np.float32)
+    got = det._post(scores, cts)
+    for b in range(B):
+        want = odet.final_kps(odet.post_process_one(scores[b], cts[b], det.trans_inv, det.out_thresh), 7)
+        assert np.array_equal(got[b], want), b
+
+
+def test_step_sequence_priors_and_decode(det):
+    """Three frames of three clips.  Every frame: (1) the prior maps the runner rendered into the engine's
+    input buffers == the reference's host rendering from the SAME detections (bit-exact); (2) the
+    detections it reports == reference post-processing of the oracle's decode of the engine's heads."""
+    from sgtapose_b200 import detector, synth
+    rng = np.random.default_rng(2)
+    det.reset()
+    q = S // 4
+    x3d = [_scene(np.random.default_rng(7), B, f) for f in range(3)]
+    for f in range(3):
+        imgs = synth.synthetic_inputs(B, S, seed=100 + f, frame=1)[0]
+        if f == 1:
+            # plant detections so that the PnP branch runs: exact projections for clip 0, two missing
+            # keypoints for clip 1, nothing detected for clip 2
+            proj = np.einsum("ij,bkj->bki", det.K, x3d[0])
+            proj = proj[:, :, :2] / proj[:, :, 2:]
+            kps = proj.copy()
+            kps[1, [2, 5]] = odet.MISSING
+            kps[2] = odet.MISSING
+            det.detected_kps = kps
+        before = det.detected_kps.copy()
+        out = det.step(imgs.pin_memory(), x3d[f - 1] if f else None, x3d[f] if f else None)
+        inp = det.eng.inp
+        for b in range(B):
+            if f == 0:
+                want = (np.zeros((S, S), np.float32),) * 2 + (np.zeros((7, q, q), np.float32),) * 2
+            else:
+                want = odet.further_inputs(before[b], x3d[f - 1][b], x3d[f][b], det.K, det.trans_input,
+                                           det.trans_output, S, q, det.raw_w, det.raw_h, detector.is_pnp)
+            got = (inp["pre_hm"][b, 0], inp["repro_hm"][b, 0], inp["pre_hm_cls"][b], inp["repro_hm_cls"][b])
+            for name, g, w in zip(("pre_hm", "repro_hm", "pre_hm_cls", "repro_hm_cls"), got, want):
+                assert np.array_equal(g.cpu().numpy(), w), (f, b, name)
+            if f == 1 and b == 0:
+                assert inp["pre_hm"][b].max().item() == 1.0 and inp["repro_hm_cls"][b].sum().item() > 7
+        heads = det.eng.out
+        ref = odec.dream_generic_decode(heads["hm"].cpu().numpy(), heads["reg"].cpu().numpy(),
+                                        heads["tracking"].cpu().numpy())
+        for b in range(B):
+            want = odet.final_kps(odet.post_process_one(np.asarray(ref["scores"][b], np.float32),
+                                                        np.asarray(ref["cts_wreg"][b], np.float32).reshape(7, 2),
+                                                        det.trans_inv, det.out_thresh), 7)
+            assert np.array_equal(out["kps_raw"][b], want), (f, b)
+        # previous image handed over on the device
+        if f:
+            assert torch.equal(inp["pre_img"], prev_x)
+        prev_x = inp["x"].clone()
+    assert det.frame == 3 and det.timing["steps"] == 3

@@ -391,6 +391,57 @@ def test_maxpool_and_upsample_add():
         assert rel_err(out.permute(0, 3, 1, 2).cpu(), ref) < 1e-5
 
 
+# ------------------------------------------------------------------------------------ prior maps
+@pytest.mark.parametrize("S", [128, 384])
+def test_render_priors_golden(golden, S):
+    """Device rendering of the four prior maps vs the reference's utilities.py outputs: bit-exact."""
+    from sgtapose_b200 import priors as PP
+    g = golden("priors.npz")
+    q = S // 4
+
+    def dense(name):
+        arr = np.zeros(tuple(g["S%d_%s_shape" % (S, name)]), np.float32)
+        arr.reshape(-1)[g["S%d_%s_idx" % (S, name)]] = g["S%d_%s_val" % (S, name)]
+        return arr
+    hm_ref, cls_ref = dense("hm"), dense("cls")
+    kps = g["S%d_kps" % S]
+    ci = PP.affine_transform_and_clip(kps, g["S%d_trans_input" % S], S, S, 640, 360)
+    co = PP.affine_transform_and_clip(kps, g["S%d_trans_output" % S], q, q, 640, 360)
+    hm = torch.full((len(kps), 1, S, S), 7.0, device=DEV)            # stale contents must be overwritten
+    cls = torch.full((len(kps), 7, q, q), 7.0, device=DEV)
+    PP.render_priors(ci, co, S, q, hm=hm, hm_cls=cls)
+    assert np.array_equal(hm[:, 0].cpu().numpy(), hm_ref)
+    assert np.array_equal(cls.cpu().numpy(), cls_ref)
+    # the per-clip wrappers with the reference's names
+    one = PP.get_prev_hm_wo_noise(kps[3], g["S%d_trans_input" % S], S, S, 640, 360, device=DEV)
+    assert np.array_equal(one.cpu().numpy(), hm_ref[3])
+    assert PP.get_prev_hm_wo_noise(None, g["S%d_trans_input" % S], S, S, 640, 360, device=DEV).abs().sum().item() == 0
+    onec = PP.get_prev_hm_wo_noise_cls(kps[2], kps[2], g["S%d_trans_output" % S], q, q, 640, 360, device=DEV)
+    assert np.array_equal(onec.cpu().numpy(), cls_ref[2])
+
+
+def test_render_priors_vs_oracle_random():
+    """Random centres incl. borders / ties, a large lock-step batch, hm-only and cls-only launches."""
+    from oracle import priors as OP
+    from sgtapose_b200 import priors as PP
+    rng = np.random.default_rng(5)
+    B, K, S, q = 37, 7, 384, 96
+    ci = rng.uniform(-2, S + 2, size=(B, K, 2)).clip(0, S - 1)
+    co = rng.uniform(-1, q + 1, size=(B, K, 2)).clip(0, q - 1)
+    ci[0, :3] = [[4.0, 4.0], [3.999, 200.0], [S - 6.0, S - 6.0]]      # first / last drawable centre, just outside
+    ci[1, :2] = [[S - 5.0, 100.0], [100.9999, 100.0]]
+    co[0] = 0                                                         # the (0,0) "not visible" marker: nothing drawn
+    hm, cls = PP.render_priors(ci, co, S, q, hm=torch.empty(B, 1, S, S, device=DEV),
+                               hm_cls=torch.empty(B, K, q, q, device=DEV))
+    for b in range(B):
+        assert np.array_equal(hm[b, 0].cpu().numpy(), OP.render_hm(ci[b], S, S)), b
+        assert np.array_equal(cls[b].cpu().numpy(), OP.render_hm_cls(co[b], q, q)), b
+    hm2, none = PP.render_priors(ci, None, S, q)
+    assert none is None and torch.equal(hm2, hm)
+    none, cls2 = PP.render_priors(None, torch.from_numpy(co).to(DEV), S, q)
+    assert none is None and torch.equal(cls2, cls)
+
+
 # ------------------------------------------------------------------------------------ whole engine
 @pytest.mark.parametrize("mode,graph", [("fp32", False), ("fp32", True)])
 def test_engine_golden(golden, mode, graph):

@@ -159,3 +159,35 @@ def test_state_dict_keys_match_reference():
     a, b = ref.state_dict(), mine.state_dict()
     assert list(a.keys()) == list(b.keys())
     assert all(a[k].shape == b[k].shape for k in a)
+
+
+# ------------------------------------------------------------------------------------ prior maps
+def _sparse_maps(g, S, name):
+    arr = np.zeros(tuple(g["S%d_%s_shape" % (S, name)]), np.float32)
+    arr.reshape(-1)[g["S%d_%s_idx" % (S, name)]] = g["S%d_%s_val" % (S, name)]
+    return arr
+
+
+@pytest.mark.parametrize("S", [128, 384])
+def test_priors_golden(golden, S):
+    """oracle/priors.py and the product's HOST helpers (affine, clip) vs the reference's own
+    utilities.py outputs (tests/golden/priors.npz, oracle/make_golden_priors.py): bit-exact."""
+    from oracle import priors as OP
+    from sgtapose_b200 import priors as PP
+    g = golden("priors.npz")
+    q = S // 4
+    c = np.array([320.0, 180.0], dtype=np.float32)
+    t_in, t_out = g["S%d_trans_input" % S], g["S%d_trans_output" % S]
+    assert np.array_equal(OP.get_affine_transform(c, 640.0, [S, S]), t_in)
+    assert np.array_equal(PP.get_affine_transform(c, 640.0, 0, [q, q]), t_out)
+    assert np.array_equal(OP.gaussian_table(), g["gaussian"])
+    assert np.array_equal(PP._G, g["gaussian"].astype(np.float32))
+    hm, cls = _sparse_maps(g, S, "hm"), _sparse_maps(g, S, "cls")
+    kps = g["S%d_kps" % S]
+    assert np.array_equal(PP.affine_transform_and_clip(kps, t_in, S, S, 640, 360), g["S%d_centres_in" % S])
+    assert np.array_equal(PP.affine_transform_and_clip(kps, t_out, q, q, 640, 360), g["S%d_centres_out" % S])
+    for i, kp in enumerate(kps):
+        assert np.array_equal(OP.affine_transform_and_clip(kp, t_in, S, S, 640, 360), g["S%d_centres_in" % S][i])
+        assert np.array_equal(OP.get_prev_hm_wo_noise(kp, t_in, S, S, 640, 360), hm[i])
+        assert np.array_equal(OP.get_prev_hm_wo_noise_cls(kp, 7, t_out, q, q, 640, 360), cls[i])
+    assert OP.get_prev_hm_wo_noise(None, t_in, S, S, 640, 360).sum() == float(g["S%d_none_hm_sum" % S])
