@@ -60,7 +60,13 @@ __device__ __forceinline__ double np_sum25(const double* a) {
   return __dadd_rn(res, a[24]);
 }
 
-// grid: B*C CTAs, 256 threads; smem: 3 maps of h*w floats + 256 Cand pairs
+// grid: B*C CTAs, 256 threads; smem: 3 maps of h*w floats + 256 Cand pairs.
+// FAST (maps up to ~100x100): the two blur passes read float64 copies of their input that are PADDED
+// with scipy's 'reflect' halo along the pass axis ((h+24) x w and h x (w+24) doubles), so the 25-tap
+// inner loop is 2 LDS.64 + DADD + DMUL + DADD per tap pair -- no index reflection (two integer modulos),
+// no float->double conversion per tap.  Same operations in the same order: results are bit-identical.
+// The kernel is bound by the fp64 pipe (37 fp64 ops per pixel and pass, no FMA contraction allowed).
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
                     const float* __restrict__ tracking, float* __restrict__ scores,
@@ -69,45 +75,111 @@ decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
                     float* __restrict__ trk, GaussW gw, int C, int h, int w) {
   extern __shared__ __align__(16) unsigned char dsm[];
   const int hw = h * w;
-  float* ori = reinterpret_cast<float*>(dsm);
-  float* tmp = ori + hw;
-  float* blr = tmp + hw;
-  Cand* cands = reinterpret_cast<Cand*>(dsm + ((sizeof(float) * 3 * hw + 15) / 16) * 16);
   __shared__ int s_count;
   const int tid = threadIdx.x;
   const int bc = blockIdx.x, b = bc / C;
   const float* src = hm + (long long)bc * hw;
   if (tid == 0) s_count = 0;
-  for (int e = tid; e < hw; e += 256) ori[e] = __ldg(src + e);
-  __syncthreads();
-
-  // pass 1: correlate along axis 0 (rows), float64 accumulate, float32 store
-  for (int e = tid; e < hw; e += 256) {
-    int y = e / w, x = e % w;
-    double t = __dmul_rn((double)ori[e], gw.w[GR]);
-#pragma unroll 4
-    for (int ii = -GR; ii < 0; ++ii) {
-      double a = (double)ori[reflect_idx(y + ii, h) * w + x];
-      double c = (double)ori[reflect_idx(y - ii, h) * w + x];
-      t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gw.w[ii + GR]));
+  float *ori, *blr;
+  Cand* cands;
+  if (FAST) {
+    double* pv = reinterpret_cast<double*>(dsm);                 // [(h + 2 GR)][w]
+    double* ph = pv + (size_t)(h + 2 * GR) * w;                  // [h][w + 2 GR]
+    blr = reinterpret_cast<float*>(ph + (size_t)h * (w + 2 * GR));
+    ori = nullptr;                                               // un-blurred values are re-read from L2
+    cands = reinterpret_cast<Cand*>(dsm);                        // aliases pv (dead after pass 1)
+    const int wp = w + 2 * GR;
+    for (int e = tid; e < (h + 2 * GR) * w; e += 256) {
+      const int yy = e / w, x = e - yy * w;
+      pv[e] = (double)__ldg(src + reflect_idx(yy - GR, h) * w + x);
     }
-    tmp[e] = (float)t;
-  }
-  __syncthreads();
-  // pass 2: along axis 1 (columns)
-  for (int e = tid; e < hw; e += 256) {
-    int y = e / w, x = e % w;
-    const float* row = tmp + y * w;
-    double t = __dmul_rn((double)row[x], gw.w[GR]);
-#pragma unroll 4
-    for (int ii = -GR; ii < 0; ++ii) {
-      double a = (double)row[reflect_idx(x + ii, w)];
-      double c = (double)row[reflect_idx(x - ii, w)];
-      t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gw.w[ii + GR]));
+    __syncthreads();
+    // pass 1: correlate along axis 0 (rows), float64 accumulate, float32 store
+    // four outputs per thread and trip: four independent DADD chains hide the fp64 latency
+    for (int e0 = tid; e0 < hw; e0 += 4 * 256) {
+      const double* c0[4];
+      double t[4];
+      int yy[4], xx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = min(e0 + u * 256, hw - 1);
+        yy[u] = e / w; xx[u] = e - yy[u] * w;
+        c0[u] = pv + (size_t)(yy[u] + GR) * w + xx[u];
+        t[u] = __dmul_rn(c0[u][0], gw.w[GR]);
+      }
+#pragma unroll
+      for (int ii = -GR; ii < 0; ++ii)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          t[u] = __dadd_rn(t[u], __dmul_rn(__dadd_rn(c0[u][ii * w], c0[u][-ii * w]), gw.w[ii + GR]));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + u * 256 < hw) ph[(size_t)yy[u] * wp + GR + xx[u]] = (double)(float)t[u];
     }
-    blr[e] = (float)t;
+    __syncthreads();
+    for (int e = tid; e < h * 2 * GR; e += 256) {                // 'reflect' halo of pass 2
+      const int y = e / (2 * GR), k = e - y * 2 * GR;
+      const int xp = k < GR ? k - GR : w + (k - GR);
+      ph[(size_t)y * wp + GR + xp] = ph[(size_t)y * wp + GR + reflect_idx(xp, w)];
+    }
+    __syncthreads();
+    // pass 2: along axis 1 (columns)
+    for (int e0 = tid; e0 < hw; e0 += 4 * 256) {
+      const double* c0[4];
+      double t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = min(e0 + u * 256, hw - 1);
+        const int y = e / w, x = e - y * w;
+        c0[u] = ph + (size_t)y * wp + GR + x;
+        t[u] = __dmul_rn(c0[u][0], gw.w[GR]);
+      }
+#pragma unroll
+      for (int ii = -GR; ii < 0; ++ii)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          t[u] = __dadd_rn(t[u], __dmul_rn(__dadd_rn(c0[u][ii], c0[u][-ii]), gw.w[ii + GR]));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + u * 256 < hw) blr[e0 + u * 256] = (float)t[u];
+    }
+    __syncthreads();
+  } else {
+    ori = reinterpret_cast<float*>(dsm);
+    float* tmp = ori + hw;
+    blr = tmp + hw;
+    cands = reinterpret_cast<Cand*>(dsm + ((sizeof(float) * 3 * hw + 15) / 16) * 16);
+    for (int e = tid; e < hw; e += 256) ori[e] = __ldg(src + e);
+    __syncthreads();
+    // pass 1: correlate along axis 0 (rows), float64 accumulate, float32 store
+    for (int e = tid; e < hw; e += 256) {
+      int y = e / w, x = e % w;
+      double t = __dmul_rn((double)ori[e], gw.w[GR]);
+#pragma unroll 4
+      for (int ii = -GR; ii < 0; ++ii) {
+        double a = (double)ori[reflect_idx(y + ii, h) * w + x];
+        double c = (double)ori[reflect_idx(y - ii, h) * w + x];
+        t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gw.w[ii + GR]));
+      }
+      tmp[e] = (float)t;
+    }
+    __syncthreads();
+    // pass 2: along axis 1 (columns)
+    for (int e = tid; e < hw; e += 256) {
+      int y = e / w, x = e % w;
+      const float* row = tmp + y * w;
+      double t = __dmul_rn((double)row[x], gw.w[GR]);
+#pragma unroll 4
+      for (int ii = -GR; ii < 0; ++ii) {
+        double a = (double)row[reflect_idx(x + ii, w)];
+        double c = (double)row[reflect_idx(x - ii, w)];
+        t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gw.w[ii + GR]));
+      }
+      blr[e] = (float)t;
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  auto orig = [&](int idx) -> float { return FAST ? __ldg(src + idx) : ori[idx]; };
 
   // peak test on the blurred map (0 outside), centroid on the un-blurred one
   Cand first, second;
@@ -129,7 +201,7 @@ decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
       for (int i = -2; i <= 2; ++i) {      // y offset -> second array index
         int f = (j + 2) * 5 + (i + 2);
         bool in = (y + i >= 0) && (y + i < h) && (x + j >= 0) && (x + j < w);
-        double wt = in ? (double)ori[(y + i) * w + (x + j)] : 0.0;
+        double wt = in ? (double)orig((y + i) * w + (x + j)) : 0.0;
         wts[f] = wt;
         xv[f] = in ? __dmul_rn((double)(x + j), wt) : 0.0;
         yv[f] = in ? __dmul_rn((double)(y + i), wt) : 0.0;
@@ -144,7 +216,7 @@ decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
       c.cx = __dadd_rn(__ddiv_rn(np_sum25(xv), scl), PEAK_OFFSET);
       c.cy = __dadd_rn(__ddiv_rn(np_sum25(yv), scl), PEAK_OFFSET);
     }
-    c.score = ori[e];
+    c.score = orig(e);
     c.pos = e;
     cand_insert(c, first, second);
   }
@@ -176,7 +248,7 @@ decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
       // shared memory against negative-weight inputs the reference would fault on
       xi = xi < 0 ? 0 : (xi > w - 1 ? w - 1 : xi);
       yi = yi < 0 ? 0 : (yi > h - 1 ? h - 1 : yi);
-      sc = ori[yi * w + xi];
+      sc = orig((int)(yi * w + xi));
     }
     long long ind = yi * w + xi;
     scores[bc] = sc; inds[bc] = ind; xs[bc] = xi; ys[bc] = yi;
@@ -357,13 +429,21 @@ extern "C" int sgta_decode_peaks(const void* hm, const void* reg, const void* tr
   SGTA_REQUIRE(hm && scores && inds && xs && ys && cts_wreg && gauss_w, "sgta_decode_peaks: null pointer");
   SGTA_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0, "sgta_decode_peaks: bad shape");
   SGTA_REQUIRE(!tracking || trk, "sgta_decode_peaks: tracking given without an output buffer");
+  GaussW gw;
+  for (int i = 0; i < 25; ++i) gw.w[i] = gauss_w[i];
+  const size_t fast = sizeof(double) * ((size_t)(h + 2 * GR) * w + (size_t)h * (w + 2 * GR)) + sizeof(float) * (size_t)h * w;
+  if (fast <= 226 * 1024 && sizeof(double) * (size_t)(h + 2 * GR) * w >= sizeof(Cand) * 512) {
+    cudaFuncSetAttribute(decode_peaks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast);
+    decode_peaks_kernel<true><<<B * C, 256, fast, (cudaStream_t)stream>>>(
+        (const float*)hm, (const float*)reg, (const float*)tracking, (float*)scores, (long long*)inds,
+        (long long*)xs, (long long*)ys, (float*)cts_wreg, (float*)trk, gw, C, h, w);
+    return check_launch("decode_peaks_kernel");
+  }
   size_t maps = ((sizeof(float) * 3 * (size_t)h * w + 15) / 16) * 16;
   size_t smem = maps + sizeof(Cand) * 512;
   SGTA_REQUIRE(smem <= 220 * 1024, "sgta_decode_peaks: heatmap %dx%d too large for shared memory", h, w);
-  GaussW gw;
-  for (int i = 0; i < 25; ++i) gw.w[i] = gauss_w[i];
-  cudaFuncSetAttribute(decode_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  decode_peaks_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>(
+  cudaFuncSetAttribute(decode_peaks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  decode_peaks_kernel<false><<<B * C, 256, smem, (cudaStream_t)stream>>>(
       (const float*)hm, (const float*)reg, (const float*)tracking, (float*)scores, (long long*)inds,
       (long long*)xs, (long long*)ys, (float*)cts_wreg, (float*)trk, gw, C, h, w);
   return check_launch("decode_peaks_kernel");
