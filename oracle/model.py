@@ -229,9 +229,11 @@ def head(sd, name, x):
 
 def forward(sd, x, pre_img, pre_hm, repro_hm, pre_hm_cls, repro_hm_cls,
             K_list=(1,) * 6, kernel_list=(12, 6, 3, 1, 1, 1), use_pos=True,
-            heads=("hm", "reg", "tracking"), tv=True, return_feats=False):
-    """-> [ {hm, reg, tracking} ] exactly like BaseModelPlanA.forward (no sigmoid)."""
-    with torch.no_grad():
+            heads=("hm", "reg", "tracking"), tv=True, return_feats=False, grad=False):
+    """-> [ {hm, reg, tracking} ] exactly like BaseModelPlanA.forward (no sigmoid).
+    grad=True keeps the autograd graph (training-step parity: the oracle for backward is torch autograd
+    through these same ops, like the reference's Trainer, trainer_parallel.py:267-284)."""
+    with torch.set_grad_enabled(grad):
         x_pre = dla34_base(sd, pre_img, pre_hm)
         x_cur = dla34_base(sd, x, repro_hm)
         fused = []

@@ -497,3 +497,50 @@ def test_engine_infer_matches_oracle_decode():
     ref = odec.dream_generic_decode(torch.sigmoid(out["hm"]).cpu().numpy(), out["reg"].cpu().numpy(),
                                     out["tracking"].cpu().numpy())
     assert np.array_equal(det["xs"].cpu().numpy(), ref["xs"]) and np.array_equal(det["ys"].cpu().numpy(), ref["ys"])
+
+
+# ------------------------------------------------------------------------------------ training step
+def test_training_step_grads_vs_oracle_autograd():
+    """BASELINE configs[4] on one GPU: forward + backward through the module tree (DCN fwd/bwd kernels,
+    attention fwd/bwd kernels, token gather/scatter) vs torch autograd through the oracle's CPU ops
+    (torchvision deform_conv2d), the way the reference's Trainer differentiates it
+    (trainer_parallel.py:267-284).  Same loss, eval-mode BN, offsets kept small (see
+    test_engine_bf16_small_offsets for why).  Bound: 2e-3 relative per parameter tensor."""
+    from sgtapose_b200 import config, networks, synth
+    S = 64
+    m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=5)
+    for k in sd:
+        if "conv_offset_mask.weight" in k:
+            sd[k] = sd[k] * 0.02
+    ins = synth.synthetic_inputs(1, S, seed=5, frame=1)
+
+    def loss_of(out):
+        return sum((o * torch.linspace(-1, 1, o.numel(), device=o.device).view_as(o)).sum() for o in out.values())
+
+    sdg = {k: (v.clone().requires_grad_() if (v.is_floating_point() and "running_" not in k) else v)
+           for k, v in sd.items()}
+    ref_out = omodel.forward(sdg, *ins, grad=True)[0]
+    ref_loss = loss_of(ref_out)
+    ref_loss.backward()
+
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    out = m(*[t.to(DEV) for t in ins])[0]
+    loss = loss_of(out)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
+    checked = 0
+    worst = ("", 0.0)
+    for name, p in m.named_parameters():
+        rg = sdg[name].grad
+        if rg is None or rg.abs().max().item() == 0.0:
+            continue
+        assert p.grad is not None, name
+        err = rel_err(p.grad.cpu(), rg)
+        if err > worst[1]:
+            worst = (name, err)
+        checked += 1
+    print("training step: %d parameter tensors compared, worst %s %.3e" % (checked, worst[0], worst[1]))
+    assert checked > 150
+    assert worst[1] < 2e-3, worst
