@@ -101,38 +101,54 @@ __global__ void pl_maxpool2_kernel(View x, View y, int C, int xc_off, int yc_off
 }
 
 // ---- y = ConvTranspose2d(C,C,2f,stride f,pad f/2,groups C)(x) + skip ---------------------------
+// grid (x blocks, row bands, B); the depth-wise kernel is staged once per CTA as [ky*k+kx][C] so a tap is
+// two LDS.128 for a thread's 8 channels (it was 32 scalar loads), and (b, oy) come from the grid
+// instead of 64-bit divisions per thread.
+constexpr int UPS_ROWS = 8;            // output rows per CTA
 template <int NS>
-__global__ void pl_upsample_add_kernel(View x, const float* __restrict__ w, View skip, int has_skip, View y, int C,
-                                    int f, long long total) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int G = C / 8;
-  const int g = (int)(e % G);
-  long long r = e / G;
-  const int ox = (int)(r % y.W); r /= y.W;
-  const int oy = (int)(r % y.H), b = (int)(r / y.H);
-  const int k = 2 * f, pad = f / 2;
-  float acc[8];
-  const long long po = frame_row(y, b, oy, ox);
-  if (has_skip) load8<NS>(skip, po, g * 8, acc);
-  else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+__global__ void __launch_bounds__(256)
+pl_upsample_add_kernel(View x, const float* __restrict__ w, View skip, int has_skip, View y, int C, int f) {
+  extern __shared__ __align__(16) float ups_w[];
+  const int k = 2 * f, pad = f / 2, kk = k * k;
+  for (int i = threadIdx.x; i < kk * C; i += 256) {
+    const int c = i % C, t = i / C;
+    ups_w[i] = __ldg(w + (long long)c * kk + t);
   }
-  const int iy_hi = (oy + pad) / f, ix_hi = (ox + pad) / f;
-  for (int iy = iy_hi; iy >= 0 && iy > iy_hi - 2; --iy) {
-    const int ky = oy + pad - iy * f;
-    if (ky >= k || iy >= x.H) continue;
-    for (int ix = ix_hi; ix >= 0 && ix > ix_hi - 2; --ix) {
-      const int kx = ox + pad - ix * f;
-      if (kx >= k || ix >= x.W) continue;
-      float v[8];
-      load8<NS>(x, frame_row(x, b, iy, ix), g * 8, v);
+  __syncthreads();
+  const int G = C >> 3;
+  const int b = blockIdx.z, oy0 = blockIdx.y * UPS_ROWS;
+  const int oy1 = min(oy0 + UPS_ROWS, y.H);
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < y.W * G; t += gridDim.x * 256) {
+    const int ox = t / G, g = t - ox * G;
+    const int ix_hi = (ox + pad) / f;
+    for (int oy = oy0; oy < oy1; ++oy) {
+      float acc[8];
+      const long long po = frame_row(y, b, oy, ox);
+      if (has_skip) load8<NS>(skip, po, g * 8, acc);
+      else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], __ldg(w + ((long long)(g * 8 + j) * k + ky) * k + kx), acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      }
+      const int iy_hi = (oy + pad) / f;
+      for (int iy = iy_hi; iy >= 0 && iy > iy_hi - 2; --iy) {
+        const int ky = oy + pad - iy * f;
+        if (ky >= k || iy >= x.H) continue;
+        for (int ix = ix_hi; ix >= 0 && ix > ix_hi - 2; --ix) {
+          const int kx = ox + pad - ix * f;
+          if (kx >= k || ix >= x.W) continue;
+          float v[8];
+          load8<NS>(x, frame_row(x, b, iy, ix), g * 8, v);
+          const float4* wt = reinterpret_cast<const float4*>(ups_w + (ky * k + kx) * C + g * 8);
+          const float4 w0 = wt[0], w1 = wt[1];
+          acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+          acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+          acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+          acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+        }
+      }
+      store8<NS>(y, po, g * 8, acc);
     }
   }
-  store8<NS>(y, po, g * 8, acc);
 }
 
 // ---- tokens -----------------------------------------------------------------------------------
@@ -155,7 +171,7 @@ __global__ void pl_gather_tokens_kernel(View x, int b_off, const long long* __re
   dst[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
 
-// One CTA per sample; token t writes iff no later token carries the same id (highest token
+// grid (samples, token chunks); token t writes iff no later token carries the same id (highest token
 // index wins: deterministic, == sequential index_put_).
 template <int NS>
 __global__ void __launch_bounds__(256)
@@ -166,7 +182,10 @@ pl_scatter_tokens_kernel(View x, int b_off, const long long* __restrict__ ids, c
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int G = C / 8;
-  for (int t = warp; t < n; t += nw) {
+  // grid.y CTAs share a sample: each takes a contiguous chunk of tokens (the duplicate scan is O(n^2))
+  const int per = (n + gridDim.y - 1) / gridDim.y;
+  const int t_end = min(n, (int)(blockIdx.y + 1) * per);
+  for (int t = blockIdx.y * per + warp; t < t_end; t += nw) {
     const int id = s_ids[t];
     bool dup = false;
     for (int u = t + 1 + lane; u < n; u += 32) dup |= (s_ids[u] == id);
@@ -245,10 +264,17 @@ extern "C" int sgta_planes_upsample_add(const sgta_planes* x, const void* w_up, 
   if (skip)
     SGTA_REQUIRE(geom_ok(skip) && skip->border == 1 && skip->nplanes == y->nplanes && skip->B == y->B &&
                  skip->H == y->H && skip->W == y->W && chan_ok(skip, 0, C), "sgta_planes_upsample_add: bad skip view");
-  const long long total = (long long)y->B * y->H * y->W * (C / 8);
   View vx = make_view(x), vy = make_view(y), vs = make_view(skip);
-  NS_DISPATCH(x->nplanes, (pl_upsample_add_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                              vx, (const float*)w_up, vs, skip != nullptr, vy, C, f, total)));
+  const size_t smem = sizeof(float) * 4 * f * f * C;
+  SGTA_REQUIRE(smem <= 96 * 1024 && y->B <= 65535, "sgta_planes_upsample_add: kernel %dx%d x %d channels too large", 2 * f, 2 * f, C);
+  int gx = cdiv((long long)y->W * (C / 8), 256);
+  if (gx > 8) gx = 8;
+  dim3 grid(gx, cdiv(y->H, UPS_ROWS), y->B);
+  NS_DISPATCH(x->nplanes, {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(pl_upsample_add_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pl_upsample_add_kernel<NS><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, (const float*)w_up, vs, skip != nullptr, vy, C, f);
+  });
   return check_launch("pl_upsample_add_kernel");
 }
 
@@ -272,7 +298,7 @@ extern "C" int sgta_planes_scatter_tokens(const sgta_planes* x, int b_off, const
   NS_DISPATCH(x->nplanes, {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(pl_scatter_tokens_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pl_scatter_tokens_kernel<NS><<<B, 256, smem, (cudaStream_t)stream>>>(v, b_off, (const long long*)ids, (const float*)rows, C, n);
+    pl_scatter_tokens_kernel<NS><<<dim3(B, cdiv(n, 96)), 256, smem, (cudaStream_t)stream>>>(v, b_off, (const long long*)ids, (const float*)rows, C, n);
   });
   return check_launch("pl_scatter_tokens_kernel");
 }
