@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 
 S = 384
 DCN_GFLOP_PER_FRAME = 7.984          # sum 2*Cout*9Cin*H*W over the 16 DCNs
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the 16 DCN launches of ONE step at the bench config
+# (fp32 mode, 32 clips): one `ncu --set full` capture, profiles/r1_ncu_full_convs_fp32_b32.txt (999.0 + 214.1 MB)
+DCN_DRAM_BYTES_PER_STEP_FP32_B32 = 1213.1e6
 TOTAL_GFLOP_PER_FRAME = 56.6
 
 
@@ -264,14 +267,16 @@ def run_ours(args):
                    "skip_dead_levels": bool(args.skip_dead_levels),
                    "engine": "eager modules + libsgta_b200" if args.engine == "eager" else
                              "InferenceEngine (NHWC, tcgen05 convs, CUDA graph)",
-                   "arithmetic": "fp32 activations, split-bf16 x3 tensor-core MMAs, fp32 accumulate"
+                   "arithmetic": "fp32 activations as fp16 hi+lo planes, 3 tensor-core MMAs per K step, rotating fp32 accumulators"
                                  if args.mode == "fp32" else "bf16 activations and MMAs, fp32 accumulate"},
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "dcn (16 launches/step)", "achieved": dcn_tflops,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": dcn_tflops / peak_tf, "traffic": None,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": dcn_tflops / peak_tf,
+                     "traffic": DCN_DRAM_BYTES_PER_STEP_FP32_B32 if (args.mode == "fp32" and B == 32 and args.engine != "eager") else None,
+                     "traffic_note": "ncu dram bytes, sum over the 16 launches of one step (achieved is also per step)",
                      "peak_source": which + " bf16 sustained", "ms_per_step": dcn_ms},
     }
     line.update(extra)
