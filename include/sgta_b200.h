@@ -278,6 +278,20 @@ int sgta_soft_argmax(const void* hm, void* out, int B, int C, int h, int w, floa
                      float size_mult, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * Post-attention half of the shared TransformerEncoderLayer, one launch per layer
+ * (sgtapose/lib/model/networks/dla.py:734-743 forward, :728-732 forward_ffn, :886-887 fc):
+ *   q1 = LayerNorm1(att fc_w^T + fc_b + q);  q2 = LayerNorm3(q1 + w2 relu(w1 q1 + b1) + b2)  -> q_out [T,C]
+ *   qp_out [T,hid] = q2 wq_next^T   (next layer's query projection; wq_next NULL = skip)
+ * att [T,hid], q [T,C], fc_wt [hid,C] (= fc.weight^T), w1 [dffn,C], w2t [dffn,C] (= linear2.weight^T),
+ * wq_next [hid,C]; fp32, row-major,
+ * C in {16,32,64}, hid % 4 == 0.  Replaces ~9 library launches (2 GEMMs through a [T,dffn] HBM
+ * intermediate, 2 LayerNorms, bias/ReLU/residual kernels). */
+int sgta_token_mlp(const void* att, const void* q, const void* fc_wt, const void* fc_b, const void* ln1_w,
+                   const void* ln1_b, const void* w1, const void* b1, const void* w2t, const void* b2,
+                   const void* ln3_w, const void* ln3_b, const void* wq_next, void* q_out, void* qp_out,
+                   int T, int C, int hid, int dffn, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Structure-prior maps: replaces the host rendering + 4 H2D copies per clip
  * and frame of lib/sgta_detector.py:528-540 (sgtapose/utilities.py:1045-1057 get_prev_hm_wo_noise,
  * :1085-1098 get_prev_hm_wo_noise_cls, :800-824 draw_umich_gaussian, :846-853 gaussian2D).

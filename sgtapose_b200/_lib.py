@@ -73,6 +73,7 @@ SIGNATURES = {
     "sgta_decode_nms_topk": (_I, [_P] * 5 + [_I] * 5 + [_P]),
     "sgta_nms3x3": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "sgta_soft_argmax": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
+    "sgta_token_mlp": (_I, [_P] * 15 + [_I] * 4 + [_F, _P]),
     "sgta_render_priors": (_I, [_P, _P, _P, _P, _c.POINTER(_F)] + [_I] * 6 + [_P]),
 }
 

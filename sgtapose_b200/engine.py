@@ -183,6 +183,13 @@ class InferenceEngine:
                     "pre_hm_cls": torch.zeros(B, 7, h2, h2, device=dev),
                     "repro_hm_cls": torch.zeros(B, 7, h2, h2, device=dev)}
 
+    def _tr(self, key):
+        """Transposed contiguous copy of a Linear weight, made once (token_mlp wants [in, out] rows)."""
+        k = key + "^T"
+        if k not in self.sd:
+            self.sd[k] = self.sd[key].float().t().contiguous()
+        return self.sd[k]
+
     # ------------------------------------------------------------------ plan pieces
     def _tree1(self, t, x, bot, resbuf, mid, cat, cout, out):
         """Tree(levels=1) (dla.py:178-231).  x: input view of tree1.conv1; bot: (pooled) input view
@@ -240,13 +247,16 @@ class InferenceEngine:
             scale = (Kp.shape[-1] // heads) ** 0.5
             pos = sd[a + ".pos_embed"] if self.use_pos else None
             q = cur_q
-            for _ in range(3):                                        # one shared layer (dla.py:788-789)
-                att = fusion.attention_core(F.linear(q, sd[a + ".w_q.weight"]), Kp, Vp, pos, heads, scale)
-                q = F.layer_norm(F.linear(att, sd[a + ".fc.weight"], sd[a + ".fc.bias"]) + q, (C,),
-                                 sd[p + ".norm1.weight"], sd[p + ".norm1.bias"])
-                ffn = F.linear(F.relu(F.linear(q, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
-                               sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
-                q = F.layer_norm(q + ffn, (C,), sd[p + ".norm3.weight"], sd[p + ".norm3.bias"])
+            qp = F.linear(q, sd[a + ".w_q.weight"])
+            for layer in range(3):                                    # one shared layer (dla.py:788-789)
+                att = fusion.attention_core(qp, Kp, Vp, pos, heads, scale)
+                # fc + residual + LN1 + FFN + residual + LN3 (+ the next layer's w_q) in one launch
+                q, qp = fusion.token_mlp(att, q, self._tr(a + ".fc.weight"), sd[a + ".fc.bias"],
+                                         sd[p + ".norm1.weight"], sd[p + ".norm1.bias"],
+                                         sd[p + ".linear1.weight"], sd[p + ".linear1.bias"],
+                                         self._tr(p + ".linear2.weight"), sd[p + ".linear2.bias"],
+                                         sd[p + ".norm3.weight"], sd[p + ".norm3.bias"],
+                                         sd[a + ".w_q.weight"] if layer < 2 else None)
             out = q
         c = "cat_layer.%d" % i
         rows = F.linear(F.relu(F.linear(torch.cat([out, cur_q], -1), sd[c + ".0.weight"], sd[c + ".0.bias"])),

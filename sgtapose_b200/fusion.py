@@ -170,3 +170,21 @@ class MHCA_ein(nn.Module):
         out = attention_core(self.w_q(query), self.w_k(key), self.w_v(value), pos, self.n_heads,
                              self.scale)
         return self.fc(out)
+
+
+def token_mlp(att, q, fc_wt, fc_b, ln1_w, ln1_b, w1, b1, w2t, b2, ln3_w, ln3_b, wq_next=None, eps=1e-5):
+    """Post-attention half of TransformerEncoderLayer.forward (dla.py:734-743) in ONE launch:
+    q2 = LN3(q1 + FFN(q1)), q1 = LN1(fc(att) + q); also the next layer's query projection w_q q2 when
+    `wq_next` is given.  att [B,n,hid], q [B,n,C] fp32 CUDA -> (q2 [B,n,C], qp [B,n,hid] | None).
+    fc_wt = fc.weight.t().contiguous() [hid,C], w2t = linear2.weight.t().contiguous() [dffn,C] (made once).
+    Inference only (no autograd): the module tree keeps the differentiable library path."""
+    B, n, C = q.shape
+    hid = att.shape[-1]
+    att, q = att.contiguous(), q.contiguous()
+    q_out = torch.empty_like(q)
+    qp = torch.empty(B, n, hid, device=q.device, dtype=torch.float32) if wq_next is not None else None
+    _lib.call("sgta_token_mlp", _lib.ptr(att), _lib.ptr(q), _lib.ptr(fc_wt), _lib.ptr(fc_b), _lib.ptr(ln1_w),
+              _lib.ptr(ln1_b), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2t), _lib.ptr(b2), _lib.ptr(ln3_w),
+              _lib.ptr(ln3_b), _lib.ptr(wq_next), _lib.ptr(q_out), _lib.ptr(qp), B * n, C, hid, w1.shape[0],
+              float(eps), _lib.stream())
+    return q_out, qp

@@ -12,6 +12,7 @@ from oracle import decode as odec
 from oracle import model as omodel
 from oracle import ref_import
 from tests import _cases as C
+from tests import _cases as C_
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -106,6 +107,31 @@ def test_attention_core_vs_torch(n, d, B):
     out2 = attention_core(q.to(DEV), k.to(DEV), v.to(DEV), None, heads, scale).cpu()
     ref2 = (torch.softmax(Q @ K.transpose(-1, -2) / scale, -1) @ V).permute(0, 2, 1, 3).reshape(B, n, heads * d)
     assert rel_err(out2, ref2) < 1e-4
+
+
+@pytest.mark.parametrize("C,n,B", [(16, 1183, 3), (32, 343, 2), (64, 63, 5)])
+def test_token_mlp_vs_torch(C, n, B):
+    """Fused fc + LN1 + FFN + LN3 (+ next w_q) vs the same torch ops in fp64 (dla.py:728-743, :886-887)."""
+    import torch.nn.functional as F
+    from sgtapose_b200.fusion import token_mlp
+    hid, dffn = 2 * C, 1024
+    att, q = C_.gen(1, B, n, hid), C_.gen(2, B, n, C)
+    fc_w, fc_b = C_.gen(3, C, hid) * 0.2, C_.gen(4, C) * 0.1
+    w1, b1 = C_.gen(5, dffn, C) * 0.2, C_.gen(6, dffn) * 0.1
+    w2, b2 = C_.gen(7, C, dffn) * 0.05, C_.gen(8, C) * 0.1
+    g1, be1, g3, be3 = C_.gen(9, C) * 0.1 + 1, C_.gen(10, C) * 0.1, C_.gen(11, C) * 0.1 + 1, C_.gen(12, C) * 0.1
+    wq = C_.gen(13, hid, C) * 0.2
+    d = lambda t: t.double()
+    q1 = F.layer_norm(F.linear(d(att), d(fc_w), d(fc_b)) + d(q), (C,), d(g1), d(be1))
+    q2 = F.layer_norm(q1 + F.linear(F.relu(F.linear(q1, d(w1), d(b1))), d(w2), d(b2)), (C,), d(g3), d(be3))
+    qp = F.linear(q2, d(wq))
+    dev = lambda *ts: [t.to(DEV) for t in ts]
+    fc_wt, w2t = fc_w.t().contiguous(), w2.t().contiguous()
+    out, outp = token_mlp(*dev(att, q, fc_wt, fc_b, g1, be1, w1, b1, w2t, b2, g3, be3), wq_next=wq.to(DEV))
+    assert rel_err(out.cpu(), q2.float()) < 2e-5
+    assert rel_err(outp.cpu(), qp.float()) < 2e-5
+    out2, none = token_mlp(*dev(att, q, fc_wt, fc_b, g1, be1, w1, b1, w2t, b2, g3, be3))
+    assert none is None and torch.equal(out2, out)
 
 
 def test_attention_backward_vs_autograd():
