@@ -179,14 +179,14 @@ static int launch_token_mlp2(TokenMlpP& p, cudaStream_t st) {
   return check_launch("token_mlp_kernel");
 }
 
-// lanes per token: enough CTAs for ~2 per SM
 template <int C>
 static int launch_token_mlp(TokenMlpP& p, cudaStream_t st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const long long want = (9ll * sms * TmThreads<C>::value) / 10;
+  // lanes per token: the largest power of two that still fits ONE wave of CTAs (one CTA per SM: the
+  // weight chunk fills shared memory), so no SM idles behind a second, mostly empty wave
   int lpt = 1;
-  while (lpt < 32 && (long long)p.T * lpt < want) lpt <<= 1;
+  while (lpt < 32 && cdiv((long long)p.T * (lpt * 2), TmThreads<C>::value) <= sms) lpt <<= 1;
   switch (lpt) {
     case 1: return launch_token_mlp2<C, 1>(p, st);
     case 2: return launch_token_mlp2<C, 2>(p, st);
