@@ -353,6 +353,57 @@ class InferenceEngine:
 
     __call__ = forward
 
+    # ------------------------------------------------------------------ pipelined host API
+    # Throughput form of `infer` for HOST inputs: the H2D copy of step i+1 runs on a copy stream into a
+    # staging set while step i computes; every step still moves its own inputs host->device and its own
+    # results device->host.      submit(step i+1 inputs) ; launch() ; collect() -> results of the launched step
+    def _pipe_init(self):
+        if getattr(self, "_pipe", None) is None:
+            dev = self.dev
+            self._pipe = {
+                "stream": torch.cuda.Stream(device=dev),
+                "stage": {k: torch.empty_like(v) for k, v in self.inp.items()},
+                "staged": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(),
+                "host": None,
+            }
+            self._pipe["free"].record(torch.cuda.current_stream(dev))
+        return self._pipe
+
+    def submit(self, x, pre_img, pre_hm, repro_hm, pre_hm_cls, repro_hm_cls):
+        """Start the host->device copy of one step's inputs (pinned host tensors) into the staging set."""
+        pp = self._pipe_init()
+        with torch.cuda.stream(pp["stream"]):
+            pp["stream"].wait_event(pp["free"])                 # the previous staged set has been consumed
+            for k, t in (("x", x), ("pre_img", pre_img), ("pre_hm", pre_hm), ("repro_hm", repro_hm),
+                         ("pre_hm_cls", pre_hm_cls), ("repro_hm_cls", repro_hm_cls)):
+                pp["stage"][k].copy_(t, non_blocking=True)
+            pp["staged"].record(pp["stream"])
+
+    def launch(self):
+        """Consume the staged inputs: D2D into the static buffers, forward + decode, async D2H of the results."""
+        pp = self._pipe_init()
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(pp["staged"])
+        for k in self.inp:
+            self.inp[k].copy_(pp["stage"][k])
+        pp["free"].record(cur)
+        dets = self.infer()
+        n = dets["scores"].shape[1]
+        packed = torch.cat([dets["scores"].view(self.B, n, 1), dets["cts_wreg"].view(self.B, n, 2),
+                            dets["tracking"].view(self.B, n, 2), dets["xs"].view(self.B, n, 1).float(),
+                            dets["ys"].view(self.B, n, 1).float()], dim=2)
+        if pp["host"] is None:
+            pp["host"] = torch.empty(packed.shape, dtype=torch.float32).pin_memory()
+        pp["host"].copy_(packed, non_blocking=True)
+        pp["done"].record(cur)
+
+    def collect(self):
+        """Results of the last launched step on the host: dict of numpy views (scores, cts_wreg, tracking, xs, ys)."""
+        pp = self._pipe_init()
+        pp["done"].synchronize()
+        r = pp["host"].numpy()
+        return {"scores": r[:, :, 0], "cts_wreg": r[:, :, 1:3], "tracking": r[:, :, 3:5], "xs": r[:, :, 5], "ys": r[:, :, 6]}
+
     def infer(self, *inputs):
         """forward -> sigmoid -> live decode, like SGTADetector.process (sgta_detector.py:881-927).
         Without arguments: on the static input buffers."""

@@ -512,6 +512,28 @@ def test_engine_bf16_small_offsets():
     assert max(errs["bf16"].values()) < 6e-2, errs
 
 
+def test_engine_pipelined_host_api():
+    """submit / launch / collect (H2D of the next step overlapping the current one) returns, step for step,
+    what the synchronous infer() returns on the same pinned host inputs."""
+    from sgtapose_b200 import config, engine, networks, synth
+    m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=3)
+    eng = engine.InferenceEngine(sd, config.default_opt(), batch=2, size=128, mode="fp32", device=DEV, fuse_sigmoid=True)
+    steps = [[t.pin_memory() for t in synth.synthetic_inputs(2, 128, seed=20 + i, frame=1)] for i in range(3)]
+    want = []
+    for ins in steps:
+        d = eng.infer(*ins)
+        want.append({k: d[k].cpu().numpy().reshape(2, 7, -1).copy() for k in ("scores", "cts_wreg", "tracking", "xs", "ys")})
+    eng.submit(*steps[0])
+    for i in range(3):
+        eng.launch()
+        if i + 1 < 3:
+            eng.submit(*steps[i + 1])
+        got = eng.collect()
+        for k in want[i]:
+            assert np.array_equal(got[k].reshape(2, 7, -1), want[i][k].astype(np.float32)), (i, k)
+
+
 def test_engine_infer_matches_oracle_decode():
     from sgtapose_b200 import config, engine, networks, synth
     m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
