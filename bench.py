@@ -318,24 +318,32 @@ def decode_roofline(dev, B=1024):
     hm = hm.to(dev).repeat(B // 64, 1, 1, 1).contiguous()
     reg = torch.rand(B, 2, 96, 96, device=dev)
     trk = torch.rand(B, 2, 96, 96, device=dev)
-    for _ in range(3):
-        decode.peaks_decode(hm, reg, trk)
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        decode.peaks_decode(hm, reg, trk)
-        e1.record()
+    def med5(**kw):
+        for _ in range(3):
+            decode.peaks_decode(hm, reg, trk, **kw)
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = sorted(ts)[2]
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            decode.peaks_decode(hm, reg, trk, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[2]
+
+    decode.recheck_count(reset=True)
+    ms = med5()
+    rechecks = decode.recheck_count(reset=True) / 8.0          # 3 warm-up + 5 timed launches
+    ms64 = med5(exact64=True)
     peaks, which = _peaks()
     gbs = hm.numel() * 4 / (ms / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": "decode_peaks_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "decode_peaks_f32_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": gbs / peaks["hbm_gbs"], "traffic": None, "frames_per_launch": B, "ms": ms,
-            "frames_per_s": B / (ms / 1e3), "peak_source": which,
-            "note": "fp64 separable blur (bit-exact scipy restatement) makes this kernel fp64-issue bound, not HBM bound"}
+            "frames_per_s": B / (ms / 1e3), "peak_source": which, "ms_all_float64_kernel": ms64,
+            "float64_rechecked_pixels_per_launch": rechecks,
+            "note": "float32 blur with a rigorous rounding band; pixels inside the band are re-evaluated with the "
+                    "bit-exact float64 scipy restatement (the all-float64 kernel is timed beside it)"}
 
 
 def clip_pipeline(eng, dev, frames):

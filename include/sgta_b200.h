@@ -263,10 +263,21 @@ int sgta_scatter_tokens(void* feats, const void* ids, const void* rows, int B, i
  *   cts_wreg [B,C,2] f32 (x_int + reg_x, y_int + reg_y; +0.5 if reg NULL),
  *   trk [B,C,2] f32 (ignored if tracking NULL)
  * gauss_w: HOST pointer to the 25 float64 blur taps (scipy _gaussian_kernel1d(3,0,12));
- * integer outputs are bit-exact w.r.t. scipy/numpy double arithmetic. */
+ * integer outputs are bit-exact w.r.t. scipy/numpy double arithmetic.
+ * The blur is evaluated in float32 and every peak comparison whose margin lies inside a
+ * rigorous rounding bound (80 * 2^-24 relative) is re-evaluated with the float64 restatement,
+ * so the result equals sgta_decode_peaks_exact64's by construction. */
 int sgta_decode_peaks(const void* hm, const void* reg, const void* tracking, void* scores,
                       void* inds, void* xs, void* ys, void* cts_wreg, void* trk,
                       const double* gauss_w, int B, int C, int h, int w, void* stream);
+/* Same contract, every pixel blurred with the float64 restatement (the cross-check of the
+ * production entry in the parity tests, and the path for maps too large for its shared memory). */
+int sgta_decode_peaks_exact64(const void* hm, const void* reg, const void* tracking, void* scores,
+                              void* inds, void* xs, void* ys, void* cts_wreg, void* trk,
+                              const double* gauss_w, int B, int C, int h, int w, void* stream);
+/* Test hook: number of pixels sgta_decode_peaks re-evaluated in float64 since the last reset
+ * (synchronises the device; count is a HOST pointer). */
+int sgta_decode_recheck_count(unsigned long long* count, int reset);
 /* Alternate decode: _nms + _topk (lib/model/utils.py:59-103; generic_decode decode.py:93-94).
  *   scores [B,K] f32, inds [B,K] int64, clses [B,K] int32; workspace >= B*C*K*12 bytes */
 int sgta_decode_nms_topk(const void* hm, void* scores, void* inds, void* clses,

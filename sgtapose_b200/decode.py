@@ -40,9 +40,17 @@ def _prep(t):
     return t.contiguous().float()
 
 
-def peaks_decode(hm, reg=None, tracking=None):
+def recheck_count(reset=True):
+    """Pixels the production decode re-evaluated in float64 since the last reset (test hook)."""
+    n = ctypes.c_uint64(0)
+    _lib.call("sgta_decode_recheck_count", ctypes.byref(n), int(reset))
+    return int(n.value)
+
+
+def peaks_decode(hm, reg=None, tracking=None, exact64=False):
     """One launch of the live decode.  Returns dict of device tensors:
-    scores [B,C] f32, inds/xs/ys [B,C] i64, cts_wreg [B,C,2] f32, tracking [B,C,2] f32|None."""
+    scores [B,C] f32, inds/xs/ys [B,C] i64, cts_wreg [B,C,2] f32, tracking [B,C,2] f32|None.
+    exact64=True runs the all-float64 cross-check kernel instead of the production one."""
     hm = _prep(hm)
     B, C, h, w = hm.shape
     reg = _prep(reg) if reg is not None else None
@@ -53,7 +61,7 @@ def peaks_decode(hm, reg=None, tracking=None):
     xs, ys = torch.empty_like(inds), torch.empty_like(inds)
     cts_wreg = torch.empty(B, C, 2, device=dev, dtype=torch.float32)
     trk = torch.empty(B, C, 2, device=dev, dtype=torch.float32) if tracking is not None else None
-    _lib.call("sgta_decode_peaks", _lib.ptr(hm), _lib.ptr(reg), _lib.ptr(tracking), _lib.ptr(scores),
+    _lib.call("sgta_decode_peaks_exact64" if exact64 else "sgta_decode_peaks", _lib.ptr(hm), _lib.ptr(reg), _lib.ptr(tracking), _lib.ptr(scores),
               _lib.ptr(inds), _lib.ptr(xs), _lib.ptr(ys), _lib.ptr(cts_wreg), _lib.ptr(trk), _GW_PTR,
               B, C, h, w, _lib.stream())
     return {"scores": scores, "inds": inds, "xs": xs, "ys": ys, "cts_wreg": cts_wreg, "tracking": trk}

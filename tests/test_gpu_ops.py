@@ -233,18 +233,83 @@ def test_decode_peaks_golden(golden):
     assert np.array_equal(d["tracking"].cpu().numpy(), g["tracking"])
 
 
-@pytest.mark.parametrize("shape", [(3, 7, 96, 96), (2, 7, 120, 120), (2, 3, 17, 40)])
+def _same_decode(a, b):
+    for k in ("xs", "ys", "inds"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(a["scores"], b["scores"])
+    assert torch.equal(a["cts_wreg"], b["cts_wreg"])
+
+
+@pytest.mark.parametrize("shape", [(3, 7, 96, 96), (2, 7, 120, 120), (2, 3, 17, 40), (1, 2, 9, 150)])
 def test_decode_peaks_vs_oracle_random(shape):
     from sgtapose_b200 import decode, synth
     B, Cc, h, w = shape
     hm, _ = synth.synthetic_heatmaps(B, Cc, h, w, seed=shape[2], noise=0.02, missing_every=4)
     hm[0, 0] = torch.rand(h, w)            # many-candidate map
     ref = odec.dream_generic_decode(hm.numpy())
+    for exact64 in (False, True):          # production (f32 blur + f64 re-check) and the all-f64 kernel
+        r = decode.peaks_decode(hm.to(DEV), exact64=exact64)
+        assert np.array_equal(r["xs"].cpu().numpy(), ref["xs"])
+        assert np.array_equal(r["ys"].cpu().numpy(), ref["ys"])
+        assert np.array_equal(r["inds"].cpu().numpy(), ref["inds"])
+        assert np.array_equal(r["scores"].cpu().numpy(), ref["scores"])
+
+
+def test_decode_peaks_recheck_paths_vs_oracle():
+    """Maps built to land inside the float32 rounding band: exact ties (symmetric twin blobs, flat
+    plateaus, a constant map that overflows the undecided list), signed maps (sign-agnostic bound),
+    values at the 0.01 threshold.  Integer outputs must still equal the oracle's."""
+    from sgtapose_b200 import decode
+    h = w = 96
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32),
+                            indexing="ij")
+
+    def blob(cx, cy, amp=0.9, s=2.0):
+        return amp * torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+
+    maps = [
+        torch.full((h, w), 0.5),                                   # every pixel ties with its neighbours
+        blob(30, 40) + blob(31, 40),                               # blurred summit shared by two pixels
+        blob(30, 40) + blob(30, 41) + blob(60, 20, amp=0.3),
+        torch.clamp(blob(50, 50, amp=3.0), max=1.0),               # saturated plateau
+        blob(20, 70) - 0.2 * blob(60, 30),                         # negative lobe: global bound
+        torch.full((h, w), 0.01),                                  # blurred value == threshold up to rounding
+        torch.full((h, w), 0.0100001),
+        blob(0, 0) + blob(95, 95, amp=0.5),                        # corners: zero-padded neighbour tests
+        torch.zeros(h, w),
+    ]
+    g = torch.Generator().manual_seed(5)
+    maps.append(0.01 + 2e-4 * torch.randn(h, w, generator=g))     # many low-contrast maxima near the threshold
+    maps.append(torch.rand(h, w, generator=g) * 1e-3 + blob(48, 48, amp=0.02, s=6.0))
+    hm = torch.stack(maps).unsqueeze(0).float()
+    ref = odec.dream_generic_decode(hm.numpy())
+    decode.recheck_count(reset=True)
     r = decode.peaks_decode(hm.to(DEV))
-    assert np.array_equal(r["xs"].cpu().numpy(), ref["xs"])
-    assert np.array_equal(r["ys"].cpu().numpy(), ref["ys"])
-    assert np.array_equal(r["inds"].cpu().numpy(), ref["inds"])
-    assert np.array_equal(r["scores"].cpu().numpy(), ref["scores"])
+    n = decode.recheck_count(reset=True)
+    assert n >= h * w                                              # the constant map alone re-checks every pixel
+    for k in ("xs", "ys", "inds", "scores"):
+        assert np.array_equal(r[k].cpu().numpy(), ref[k]), k
+    _same_decode(r, decode.peaks_decode(hm.to(DEV), exact64=True))
+
+
+def test_decode_peaks_full_size_production_equals_exact64():
+    """BASELINE size of the decode-only leg (1024 frames x 7 maps): the production kernel and the
+    all-float64 kernel agree on every output, and the float64 re-check stays rare."""
+    from sgtapose_b200 import decode, synth
+    hm, _ = synth.synthetic_heatmaps(1024, 7, 96, 96, seed=11, noise=0.005, missing_every=5)
+    g = torch.Generator().manual_seed(3)
+    hm[:64] = 0.0105 + 3e-4 * torch.randn(64, 7, 96, 96, generator=g)   # random-init-like heads
+    reg = torch.rand(1024, 2, 96, 96, generator=g)
+    trk = torch.randn(1024, 2, 96, 96, generator=g)
+    hm, reg, trk = hm.to(DEV), reg.to(DEV), trk.to(DEV)
+    decode.recheck_count(reset=True)
+    a = decode.peaks_decode(hm, reg, trk)
+    n = decode.recheck_count(reset=True)
+    b = decode.peaks_decode(hm, reg, trk, exact64=True)
+    _same_decode(a, b)
+    assert torch.equal(a["tracking"], b["tracking"])
+    assert n < 1024 * 7 * 4, n                                      # a handful per map, not thousands
+    assert (a["scores"] >= 0).float().mean() > 0.5                 # most keypoints found
 
 
 def test_nms_topk_softargmax_golden(golden):
