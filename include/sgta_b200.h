@@ -316,6 +316,20 @@ int sgta_token_mlp(const void* att, const void* q, const void* fc_wt, const void
 int sgta_render_priors(const void* centres_in, const void* centres_out, void* hm, void* hm_cls,
                        const float* gauss9x9, int B, int K, int H, int W, int h, int w, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Image pre-processing: SGTADetector.pre_process
+ * (sgtapose/lib/sgta_detector.py:368-399) = cv2.warpAffine(image, trans_input, (W, H), INTER_LINEAR)
+ * (:381-383) + ((img / 255.) - mean) / std in float32 and HWC -> CHW (:384-386, :402-403), for B frames.
+ *   img_u8 [B,h,w,3] uint8 DEVICE (raw frames as cv2.imread returns them)
+ *   out    [B,3,H,W] fp32 DEVICE (network input)
+ *   out_u8 [B,H,W,3] uint8 DEVICE or NULL: the warped 8-bit image (bit-exact vs cv2, for parity tests)
+ *   trans  HOST pointer, n_trans x 6 float64: the FORWARD 2x3 matrices the reference passes to
+ *          cv2.warpAffine (trans_input); n_trans = 1 (shared by all frames) or B
+ *   mean3 / std3  HOST pointers, 3 floats (sgta_detector.py:58-59)
+ * 8-bit results are bit-exact w.r.t. OpenCV's fixed-point bilinear remap (BORDER_CONSTANT 0). */
+int sgta_preprocess(const void* img_u8, void* out, void* out_u8, const double* trans, int n_trans,
+                    const float* mean3, const float* std3, int B, int h, int w, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,7 +359,7 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
                         float* __restrict__ trk, const __grid_constant__ GaussW gw,
                         const __grid_constant__ GaussWF gf, int C, int h, int w, int plane_floats) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  __shared__ int s_count, s_nund, s_min_ok;
+  __shared__ int s_count, s_nund, s_nacc, s_min_ok;
   __shared__ float s_max[8];
   __shared__ int s_list[UND_CAP];                       // undecided pixels (row-major position)
   __shared__ float s_t[3 * 32];                         // re-check: exact pass-1 values, 3 rows x 27
@@ -371,7 +371,7 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
   float* bufA = reinterpret_cast<float*>(dsm);
   float* bufB = bufA + plane_floats;
   Cand* cands = reinterpret_cast<Cand*>(bufB);          // aliases bufB (dead once the scans are done)
-  if (tid == 0) { s_count = 0; s_nund = 0; s_min_ok = 1; }
+  if (tid == 0) { s_count = 0; s_nund = 0; s_nacc = 0; s_min_ok = 1; }
   __syncthreads();
 
   // phase 0
@@ -417,12 +417,21 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
 #pragma unroll
       for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = bufA[refl(y0 - GR + r, h) * w + x];
     }
+    float a[SEG];                                               // SEG independent chains: tap-major order
 #pragma unroll
-    for (int k = 0; k < SEG; ++k) {
-      float a = in[k] * gf.w[0];
+    for (int k = 0; k < SEG; ++k) a[k] = in[k] * gf.w[0];
 #pragma unroll
-      for (int t = 1; t < 2 * GR + 1; ++t) a = fmaf(in[k + t], gf.w[t], a);
-      if (y0 + k < h) bufB[(y0 + k) * wp + x] = a;
+    for (int t = 1; t < 2 * GR + 1; ++t)
+#pragma unroll
+      for (int k = 0; k < SEG; ++k) a[k] = fmaf(in[k + t], gf.w[t], a[k]);
+    float* ocol = bufB + y0 * wp + x;
+    if (y0 + SEG <= h) {
+#pragma unroll
+      for (int k = 0; k < SEG; ++k) ocol[k * wp] = a[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < SEG; ++k)
+        if (y0 + k < h) ocol[k * wp] = a[k];
     }
   }
   __syncthreads();
@@ -441,57 +450,61 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
       for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[refl(x0 - GR + r, w)];
     }
     float* orow = bufA + y * wp + x0;
+    float a[SEG];
 #pragma unroll
-    for (int k = 0; k < SEG; ++k) {
-      float a = in[k] * gf.w[0];
+    for (int k = 0; k < SEG; ++k) a[k] = in[k] * gf.w[0];
 #pragma unroll
-      for (int t = 1; t < 2 * GR + 1; ++t) a = fmaf(in[k + t], gf.w[t], a);
-      if (x0 + k < w) orow[k] = a;
+    for (int t = 1; t < 2 * GR + 1; ++t)
+#pragma unroll
+      for (int k = 0; k < SEG; ++k) a[k] = fmaf(in[k + t], gf.w[t], a[k]);
+    if (x0 + SEG <= w) {
+#pragma unroll
+      for (int k = 0; k < SEG; ++k) orow[k] = a[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < SEG; ++k)
+        if (x0 + k < w) orow[k] = a[k];
     }
   }
   __syncthreads();
 
-  // phase 3: scan.  Round 0 tests the float32 blur with margins; if more than UND_CAP pixels fall inside
-  // the rounding band (flat or constant maps) the whole map is re-blurred in float64 and round 1 applies
-  // the reference predicate to exact values.
+  // phase 3: scan.  Round 0 tests the float32 blur with margins: accepted peaks and undecided pixels go to
+  // shared-memory lists (the loop itself stays light); if more than UND_CAP pixels fall inside the rounding
+  // band (flat or constant maps) the whole map is re-blurred in float64 and round 1 applies the reference
+  // predicate to exact values.
   auto orig = [&](int idx) -> float { return __ldg(src + idx); };
-  Cand first, second;
-  int mine;
+  int* acc_list = reinterpret_cast<int*>(bufB);                 // <= h*w accepted peaks; bufB is dead here
   bool exact_mode = false;
   for (;;) {
-    first.pos = second.pos = 0x7fffffff;
-    first.cx = first.cy = second.cx = second.cy = 0.0;
-    first.score = second.score = 0.f;
-    mine = 0;
+    const float er = exact_mode ? 0.f : (nonneg ? ERR_BOUND : 0.f);   // |v - v_ref| <= er * v + ea
+    const float ea = exact_mode ? 0.f : (nonneg ? 0.f : EM);
     for (int y = warp; y < h; y += 8) {
-      for (int x = lane; x < w; x += 32) {
-        const float* p = bufA + y * wp + x;
+      const float* p = bufA + y * wp + lane;
+      for (int x = lane; x < w; x += 32, p += 32) {
         const float v = *p;
-        const float ev = exact_mode ? 0.f : (nonneg ? ERR_BOUND * v : EM);   // |v - v_ref| <= ev
+        const float ev = fmaf(er, v, ea);
         if (v < BLUR_THRESH - ev) continue;                     // surely not above the threshold
         const float nb[4] = {y > 0 ? p[-wp] : 0.f, y < h - 1 ? p[wp] : 0.f, x > 0 ? p[-1] : 0.f,
                              x < w - 1 ? p[1] : 0.f};
-        if (exact_mode) {                                       // image_proc.py:1054-1073 on exact values
-          if (!(v > BLUR_THRESH && v >= nb[0] && v >= nb[1] && v >= nb[2] && v >= nb[3])) continue;
-        } else {
-          bool sure = v > BLUR_THRESH + ev, drop = false;
+        bool sure = v > BLUR_THRESH + ev, drop = false;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float band = ev + (nonneg ? ERR_BOUND * nb[k] : EM);
-            const float d = v - nb[k];
-            drop = drop || d < -band;                           // surely below a neighbour
-            sure = sure && d > band;
-          }
-          if (drop) continue;
-          if (!sure) {                                          // inside the rounding band (or NaN/Inf)
+        for (int k = 0; k < 4; ++k) {
+          const float band = ev + fmaf(er, nb[k], ea);
+          const float d = v - nb[k];
+          drop = drop || d < -band;                             // surely below a neighbour
+          sure = sure && d > band;
+        }
+        if (drop) continue;
+        if (!sure) {                                            // inside the rounding band, a tie, or NaN/Inf
+          if (exact_mode) {                                     // image_proc.py:1054-1073 on exact values
+            if (!(v > BLUR_THRESH && v >= nb[0] && v >= nb[1] && v >= nb[2] && v >= nb[3])) continue;
+          } else {
             const int slot = atomicAdd(&s_nund, 1);
             if (slot < UND_CAP) s_list[slot] = y * w + x;       // re-checked by the whole CTA below
             continue;
           }
         }
-        ++mine;
-        Cand c = make_cand(orig, y, x, h, w);
-        cand_insert(c, first, second);
+        acc_list[atomicAdd(&s_nacc, 1)] = y * w + x;
       }
     }
     __syncthreads();
@@ -505,6 +518,7 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
       const int y = e / w, x = e - y * w;
       bufA[y * wp + x] = exact_pass2(bufB + y * wp, x, w, gw);
     }
+    if (tid == 0) s_nacc = 0;
     __syncthreads();
     exact_mode = true;
   }
@@ -537,15 +551,22 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
     if (tid == 0) {
       const float ve = s_v[0];
       const bool pk = ve > BLUR_THRESH && ve >= s_v[1] && ve >= s_v[2] && ve >= s_v[3] && ve >= s_v[4];
-      if (!pk) s_list[i] = -1;
+      if (pk) acc_list[s_nacc++] = e;                           // only this thread touches the list here
     }
   }
   __syncthreads();
-  for (int i = tid; i < nund; i += 256) {
-    const int e = s_list[i];
-    if (e < 0) continue;
+
+  // centroids of the accepted peaks, spread over the CTA
+  Cand first, second;
+  first.pos = second.pos = 0x7fffffff;
+  first.cx = first.cy = second.cx = second.cy = 0.0;
+  first.score = second.score = 0.f;
+  int mine = 0;
+  const int nacc = s_nacc;
+  for (int i = tid; i < nacc; i += 256) {
+    const int e = acc_list[i], y = e / w;
     ++mine;
-    Cand c = make_cand(orig, e / w, e % w, h, w);
+    Cand c = make_cand(orig, y, e - y * w, h, w);
     cand_insert(c, first, second);
   }
   if (tid == 0 && s_nund) atomicAdd(&g_exact_rechecks, (unsigned long long)(exact_mode ? hw : s_nund));

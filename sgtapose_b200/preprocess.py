@@ -1,0 +1,96 @@
+"""Image pre-processing on the device for a lock-step batch of clips.
+
+Mirrors `SGTADetector._transform_scale` / `pre_process` / `normalize_img`
+(sgtapose/lib/sgta_detector.py:334-366, :368-399, :402-403) for the `fix_res` testing mode the
+reference runs in (opts_parallel.py:341): same `meta` keys, same matrices (the 3-point solve stays
+`cv2.getAffineTransform` on the host through `get_affine_transform`, lib/utils/image.py:45-78), and
+the network input computed by ONE launch of `sgta_preprocess` from the raw uint8 frames -- cv2's
+fixed-point bilinear warp restated bit-exactly, then ((img / 255.) - mean) / std in float32.
+
+The reference uploads a float32 [1,3,H,W] tensor per frame (:154); here the raw frames travel as
+uint8 (h*w*3 bytes instead of H*W*12).  No CPU fallback: inputs must reach the device.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MEAN = (0.5, 0.5, 0.5)      # sgta_detector.py:58
+STD = (0.5, 0.5, 0.5)       # sgta_detector.py:59
+
+
+def get_affine_transform(center, scale, rot, output_size, shift=np.array([0, 0], dtype=np.float32), inv=0):
+    """lib/utils/image.py:45-78 (same signature): 2x3 float64 matrix through cv2.getAffineTransform."""
+    import cv2
+    if not isinstance(scale, np.ndarray) and not isinstance(scale, list):
+        scale = np.array([scale, scale], dtype=np.float32)
+    src_w, dst_w, dst_h = scale[0], output_size[0], output_size[1]
+    rot_rad = np.pi * rot / 180
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    p = [0, src_w * -0.5]
+    src_dir = np.array([p[0] * cs - p[1] * sn, p[0] * sn + p[1] * cs])          # get_dir, image.py:92-100
+    dst_dir = np.array([0, dst_w * -0.5], np.float32)
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = center + scale * shift
+    src[1, :] = center + src_dir + scale * shift
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5], np.float32) + dst_dir
+    for pts in (src, dst):                                                       # get_3rd_point, image.py:87-89
+        d = pts[0] - pts[1]
+        pts[2] = pts[1] + np.array([-d[1], d[0]], dtype=np.float32)
+    if inv:
+        return cv2.getAffineTransform(np.float32(dst), np.float32(src))
+    return cv2.getAffineTransform(np.float32(src), np.float32(dst))
+
+
+def transform_meta(height, width, opt):
+    """_transform_scale (fix_res branch, scale 1) + the meta dict of pre_process for one raw frame size."""
+    if getattr(opt, "fix_short", -1) > 0 or not getattr(opt, "fix_res", True):
+        raise _lib.SgtaError("pre_process: only the fix_res testing mode of the reference is built")
+    inp_h, inp_w = int(opt.input_h), int(opt.input_w)
+    c = np.array([width / 2., height / 2.], dtype=np.float32)
+    s = max(height, width) * 1.0
+    down = int(getattr(opt, "down_ratio", 4))
+    out_h, out_w = inp_h // down, inp_w // down
+    return {"c": c, "s": s, "height": height, "width": width, "out_height": out_h, "out_width": out_w,
+            "inp_height": inp_h, "inp_width": inp_w,
+            "trans_input": get_affine_transform(c, s, 0, [inp_w, inp_h]),
+            "trans_output": get_affine_transform(c, s, 0, [out_w, out_h])}
+
+
+def warp_normalize(frames_u8, trans, out_hw, mean=MEAN, std=STD, return_u8=False):
+    """frames_u8 [B,h,w,3] uint8 CUDA, trans [6] / [2,3] (shared) or [B,2,3] forward matrices
+    -> network input [B,3,H,W] float32 (and the warped uint8 image [B,H,W,3] if asked)."""
+    if not frames_u8.is_cuda:
+        raise _lib.SgtaError("pre_process: frames must be CUDA tensors (no CPU fallback)")
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
+        raise _lib.SgtaError("pre_process: frames must be uint8 [B,h,w,3]")
+    frames_u8 = frames_u8.contiguous()
+    B, h, w, _ = frames_u8.shape
+    H, W = int(out_hw[0]), int(out_hw[1])
+    t = np.ascontiguousarray(np.asarray(trans, np.float64).reshape(-1, 6))
+    out = torch.empty(B, 3, H, W, device=frames_u8.device, dtype=torch.float32)
+    u8 = torch.empty(B, H, W, 3, device=frames_u8.device, dtype=torch.uint8) if return_u8 else None
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.call("sgta_preprocess", _lib.ptr(frames_u8), _lib.ptr(out), _lib.ptr(u8),
+              t.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), t.shape[0], m3, s3, B, h, w, H, W, _lib.stream())
+    return (out, u8) if return_u8 else out
+
+
+def pre_process(frames, opt, device="cuda"):
+    """SGTADetector.pre_process for B frames of one raw size.
+    frames: uint8 [B,h,w,3] (numpy or torch, host or device; host frames are uploaded as uint8).
+    -> (images [B,3,H,W] float32 on the device, meta)."""
+    if isinstance(frames, np.ndarray):
+        frames = torch.from_numpy(np.ascontiguousarray(frames))
+    if frames.dim() == 3:
+        frames = frames.unsqueeze(0)
+    if not frames.is_cuda:
+        frames = frames.to(device, non_blocking=True)
+    meta = transform_meta(int(frames.shape[1]), int(frames.shape[2]), opt)
+    images = warp_normalize(frames, meta["trans_input"], (meta["inp_height"], meta["inp_width"]))
+    return images, meta
