@@ -357,7 +357,10 @@ def clip_pipeline(eng, dev, frames):
     B = eng.B
     rng = np.random.default_rng(317)
     base = rng.uniform([-0.35, -0.2, 1.2], [0.35, 0.2, 1.8], size=(B, 7, 3))
-    imgs = [synth.synthetic_inputs(B, S, seed=400 + f, frame=1)[0].pin_memory() for f in range(2)]
+    # RAW camera frames (uint8 640x360, what the reference's run() receives): uploaded as uint8 and
+    # pre-processed on the device (warpAffine + normalise, sgta_detector.py:368-399) inside every step
+    imgs = [torch.from_numpy(rng.integers(0, 256, (B, det.raw_h, det.raw_w, 3), dtype=np.uint8)).pin_memory()
+            for f in range(2)]
 
     def x3d(f):
         return base + 0.004 * f
@@ -379,7 +382,8 @@ def clip_pipeline(eng, dev, frames):
     return {"frames_per_s": B * frames / dt, "frames": frames, "clips": B, "ms_per_step": dt / frames * 1e3,
             "host_pnp_render_ms_per_step": det.timing["host_pnp"] / frames * 1e3,
             "host_post_ms_per_step": det.timing["host_post"] / frames * 1e3,
-            "h2d_bytes_per_step": imgs[0].numel() * 4 + 2 * 2 * B * 7 * 2 * 8, "d2h_bytes_per_step": B * 7 * 3 * 4}
+            "input": "raw uint8 %dx%d frames, device pre-processing" % (det.raw_w, det.raw_h),
+            "h2d_bytes_per_step": imgs[0].numel() + 2 * 2 * B * 7 * 2 * 8, "d2h_bytes_per_step": B * 7 * 3 * 4}
 
 
 def time_dcn_kernels(fn):

@@ -124,7 +124,6 @@ __device__ __forceinline__ void reduce_and_emit(Cand first, Cand second, int min
     bool found = false;
     if (count == 1) found = true;
     else if (count > 1) found = (a.score - s2.score) >= AMBIG_GAP;   // float32 subtraction
-    float sc = -1.f;
     long long xi = 0, yi = 0;
     if (found) {
       xi = (long long)a.cx;   // int(): truncation toward zero
@@ -133,20 +132,17 @@ __device__ __forceinline__ void reduce_and_emit(Cand first, Cand second, int min
       // the gathers against negative-weight inputs the reference would fault on
       xi = xi < 0 ? 0 : (xi > w - 1 ? w - 1 : xi);
       yi = yi < 0 ? 0 : (yi > h - 1 ? h - 1 : yi);
-      sc = orig((int)(yi * w + xi));
     }
-    long long ind = yi * w + xi;
-    scores[bc] = sc; inds[bc] = ind; xs[bc] = xi; ys[bc] = yi;
-    float fx = (float)xi, fy = (float)yi;
-    if (reg) {
-      const float* rb = reg + (long long)b * 2 * hw;
-      fx += __ldg(rb + ind); fy += __ldg(rb + hw + ind);
-    } else { fx += 0.5f; fy += 0.5f; }
-    cts_wreg[2 * bc] = fx; cts_wreg[2 * bc + 1] = fy;
-    if (tracking && trk) {
-      const float* tb = tracking + (long long)b * 2 * hw;
-      trk[2 * bc] = __ldg(tb + ind); trk[2 * bc + 1] = __ldg(tb + hw + ind);
-    }
+    const long long ind = yi * w + xi;
+    // the five gathers depend on `ind` only: issue them together (one L2 round trip, not three)
+    const float* rb = reg ? reg + (long long)b * 2 * hw : nullptr;
+    const float* tb = (tracking && trk) ? tracking + (long long)b * 2 * hw : nullptr;
+    const float sv = orig((int)ind);
+    const float r0 = rb ? __ldg(rb + ind) : 0.5f, r1 = rb ? __ldg(rb + hw + ind) : 0.5f;
+    const float t0 = tb ? __ldg(tb + ind) : 0.f, t1 = tb ? __ldg(tb + hw + ind) : 0.f;
+    scores[bc] = found ? sv : -1.f; inds[bc] = ind; xs[bc] = xi; ys[bc] = yi;
+    cts_wreg[2 * bc] = (float)xi + r0; cts_wreg[2 * bc + 1] = (float)yi + r1;
+    if (tb) { trk[2 * bc] = t0; trk[2 * bc + 1] = t1; }
   }
 }
 
@@ -327,6 +323,12 @@ __device__ __forceinline__ int refl(int i, int n) {
   return r;
 }
 
+// one fold, branch-free: valid for -n <= i < 2n (maps of at least SEG + 2*GR rows / columns)
+__device__ __forceinline__ int refl1(int i, int n) {
+  i = i < 0 ? -1 - i : i;
+  return i >= n ? 2 * n - 1 - i : i;
+}
+
 // exact restatement of one output of pass 1 (reads the un-blurred map from global memory) and of
 // pass 2 (reads a row of exact pass-1 values): same operations and order as decode_peaks_kernel
 __device__ __noinline__ float exact_pass1(const float* __restrict__ src, int y, int x, int h, int w,
@@ -413,6 +415,9 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
       const float* col = bufA + (y0 - GR) * w + x;
 #pragma unroll
       for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = col[r * w];
+    } else if (h >= SEG + 2 * GR) {                             // first / last segments: one fold
+#pragma unroll
+      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = bufA[refl1(y0 - GR + r, h) * w + x];
     } else {
 #pragma unroll
       for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = bufA[refl(y0 - GR + r, h) * w + x];
@@ -445,6 +450,9 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
     if (x0 >= GR && x0 + SEG + GR <= w) {
 #pragma unroll
       for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[x0 - GR + r];
+    } else if (w >= SEG + 2 * GR) {
+#pragma unroll
+      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[refl1(x0 - GR + r, w)];
     } else {
 #pragma unroll
       for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[refl(x0 - GR + r, w)];

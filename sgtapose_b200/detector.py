@@ -16,8 +16,10 @@ all about WHERE things run, none about what is computed:
   * the per-clip PnP (cv2, host, as north_star wants) runs on a thread pool -- cv2 releases the GIL.
 
 Keypoint 3-D positions w.r.t. the camera for the previous / current frame are inputs (the
-reference reads them from the frame JSONs, sgta_detector.py:511-517).  Image pre-processing
-(cv2 warpAffine + normalise, :368-399) is outside this module: `step` takes network-input images.
+reference reads them from the frame JSONs, sgta_detector.py:511-517).  `step` takes either
+network-input images (float32) or the RAW uint8 frames: those are uploaded as uint8 and pre-processed
+on the device (cv2 warpAffine + normalise, :368-399 -> preprocess.py, bit-exact) straight into the
+engine's input buffer.
 """
 import concurrent.futures as cf
 import time
@@ -25,6 +27,7 @@ import time
 import numpy as np
 import torch
 
+from . import preprocess as PP
 from . import priors as PR
 
 MISSING = -999.999 * 4          # sgta_detector.py:613, :521
@@ -140,20 +143,34 @@ class LockstepDetector:
 
     # ------------------------------------------------------------------ one frame of every clip
     def step(self, images, x3d_prev=None, x3d_next=None):
-        """images [B,3,S,S] fp32 (device or pinned host).  x3d_prev / x3d_next: [B,n_kp,3] keypoint
+        """images [B,3,S,S] fp32 (device or pinned host), or raw frames [B,raw_h,raw_w,3] uint8 (numpy / torch,
+        host or device) that are pre-processed on the device.  x3d_prev / x3d_next: [B,n_kp,3] keypoint
         positions w.r.t. the camera in the previous / this frame (ignored at frame 0).
         Returns {'kps_raw' [B,n_kp,2] float64 (MISSING = not detected), 'scores' [B,n_kp]}."""
         eng, inp = self.eng, self.eng.inp
         t0 = time.perf_counter()
+        if isinstance(images, np.ndarray):
+            images = torch.from_numpy(images)
+        raw = images.dtype == torch.uint8
+
+        def load_x():
+            if raw:                                              # pre_process (:368-399) on the device
+                if tuple(images.shape[1:]) != (self.raw_h, self.raw_w, 3):
+                    raise ValueError("raw frames must be [B,%d,%d,3] uint8" % (self.raw_h, self.raw_w))
+                PP.warp_normalize(images.to(inp["x"].device, non_blocking=True), self.trans_input,
+                                  (self.S, self.S), out=inp["x"])
+            else:
+                inp["x"].copy_(images, non_blocking=True)
+
         if self.frame == 0:
             # _get_additional_inputs (:415-454): all-zero priors, pre_images = images (:157-159)
             for k in ("pre_hm", "repro_hm", "pre_hm_cls", "repro_hm_cls"):
                 inp[k].zero_()
-            inp["x"].copy_(images, non_blocking=True)
+            load_x()
             inp["pre_img"].copy_(inp["x"])
         else:
             inp["pre_img"].copy_(inp["x"])                       # self.pre_images = images (:204)
-            inp["x"].copy_(images, non_blocking=True)
+            load_x()
             jobs = [(b, x3d_prev[b], x3d_next[b]) for b in range(self.B)]
             res = list(self.pool.map(lambda a: self._clip_centres(*a), jobs)) if self.pool else \
                 [self._clip_centres(*a) for a in jobs]

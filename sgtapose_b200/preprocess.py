@@ -16,34 +16,14 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import priors as PR
 
 MEAN = (0.5, 0.5, 0.5)      # sgta_detector.py:58
 STD = (0.5, 0.5, 0.5)       # sgta_detector.py:59
 
 
-def get_affine_transform(center, scale, rot, output_size, shift=np.array([0, 0], dtype=np.float32), inv=0):
-    """lib/utils/image.py:45-78 (same signature): 2x3 float64 matrix through cv2.getAffineTransform."""
-    import cv2
-    if not isinstance(scale, np.ndarray) and not isinstance(scale, list):
-        scale = np.array([scale, scale], dtype=np.float32)
-    src_w, dst_w, dst_h = scale[0], output_size[0], output_size[1]
-    rot_rad = np.pi * rot / 180
-    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
-    p = [0, src_w * -0.5]
-    src_dir = np.array([p[0] * cs - p[1] * sn, p[0] * sn + p[1] * cs])          # get_dir, image.py:92-100
-    dst_dir = np.array([0, dst_w * -0.5], np.float32)
-    src = np.zeros((3, 2), dtype=np.float32)
-    dst = np.zeros((3, 2), dtype=np.float32)
-    src[0, :] = center + scale * shift
-    src[1, :] = center + src_dir + scale * shift
-    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
-    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5], np.float32) + dst_dir
-    for pts in (src, dst):                                                       # get_3rd_point, image.py:87-89
-        d = pts[0] - pts[1]
-        pts[2] = pts[1] + np.array([-d[1], d[0]], dtype=np.float32)
-    if inv:
-        return cv2.getAffineTransform(np.float32(dst), np.float32(src))
-    return cv2.getAffineTransform(np.float32(src), np.float32(dst))
+# lib/utils/image.py:45-78 and utilities.py:889-925 are the same function in the reference: one host restatement
+get_affine_transform = PR.get_affine_transform
 
 
 def transform_meta(height, width, opt):
@@ -61,9 +41,10 @@ def transform_meta(height, width, opt):
             "trans_output": get_affine_transform(c, s, 0, [out_w, out_h])}
 
 
-def warp_normalize(frames_u8, trans, out_hw, mean=MEAN, std=STD, return_u8=False):
+def warp_normalize(frames_u8, trans, out_hw, mean=MEAN, std=STD, return_u8=False, out=None):
     """frames_u8 [B,h,w,3] uint8 CUDA, trans [6] / [2,3] (shared) or [B,2,3] forward matrices
-    -> network input [B,3,H,W] float32 (and the warped uint8 image [B,H,W,3] if asked)."""
+    -> network input [B,3,H,W] float32 (and the warped uint8 image [B,H,W,3] if asked).
+    `out`: an existing contiguous [B,3,H,W] float32 CUDA tensor to write into (the engine's input buffer)."""
     if not frames_u8.is_cuda:
         raise _lib.SgtaError("pre_process: frames must be CUDA tensors (no CPU fallback)")
     if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
@@ -72,7 +53,10 @@ def warp_normalize(frames_u8, trans, out_hw, mean=MEAN, std=STD, return_u8=False
     B, h, w, _ = frames_u8.shape
     H, W = int(out_hw[0]), int(out_hw[1])
     t = np.ascontiguousarray(np.asarray(trans, np.float64).reshape(-1, 6))
-    out = torch.empty(B, 3, H, W, device=frames_u8.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(B, 3, H, W, device=frames_u8.device, dtype=torch.float32)
+    elif tuple(out.shape) != (B, 3, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise _lib.SgtaError("pre_process: `out` must be a contiguous float32 [B,3,H,W] tensor")
     u8 = torch.empty(B, H, W, 3, device=frames_u8.device, dtype=torch.uint8) if return_u8 else None
     m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s3 = (ctypes.c_float * 3)(*[float(v) for v in std])

@@ -87,3 +87,21 @@ def test_step_sequence_priors_and_decode(det):
             assert torch.equal(inp["pre_img"], prev_x)
         prev_x = inp["x"].clone()
     assert det.frame == 3 and det.timing["steps"] == 3
+
+
+def test_step_accepts_raw_uint8_frames(det):
+    """Raw 640x360 uint8 frames pre-processed on the device == the oracle's pre_process of the same frames
+    fed as float32 network inputs: identical input buffer and identical detections."""
+    from oracle import preprocess as opre
+    from oracle.make_golden_preprocess import case_image
+    frames = np.stack([case_image((det.raw_h, det.raw_w), 40 + b) for b in range(B)])
+    want_x = np.concatenate([opre.pre_process(frames[b], S, S)[0] for b in range(B)])
+    det.reset()
+    out_raw = det.step(frames)
+    assert np.array_equal(det.eng.inp["x"].cpu().numpy(), want_x)
+    assert torch.equal(det.eng.inp["pre_img"], det.eng.inp["x"])
+    det.reset()
+    out_f32 = det.step(torch.from_numpy(want_x).pin_memory())
+    assert np.array_equal(out_raw["kps_raw"], out_f32["kps_raw"]) and np.array_equal(out_raw["scores"], out_f32["scores"])
+    with pytest.raises(ValueError):
+        det.step(frames[:, :100])

@@ -191,3 +191,51 @@ def test_priors_golden(golden, S):
         assert np.array_equal(OP.get_prev_hm_wo_noise(kp, t_in, S, S, 640, 360), hm[i])
         assert np.array_equal(OP.get_prev_hm_wo_noise_cls(kp, 7, t_out, q, q, 640, 360), cls[i])
     assert OP.get_prev_hm_wo_noise(None, t_in, S, S, 640, 360).sum() == float(g["S%d_none_hm_sum" % S])
+
+
+# ------------------------------------------------------------------------------------ pre-processing
+def test_preprocess_oracle_matches_reference_golden(golden):
+    """oracle/preprocess.py vs the reference's own pre_process output (oracle/make_golden_preprocess.py)."""
+    from oracle import preprocess as opre
+    from oracle.make_golden_preprocess import CASES, case_image
+    g = golden("preprocess.npz")
+    for i, (raw, inp, seed) in enumerate(CASES):
+        images, meta, _ = opre.pre_process(case_image(raw, seed), inp[0], inp[1])
+        assert np.array_equal(images, g["images_%d" % i]), i                   # float32 bit-exact
+        assert np.array_equal(meta["trans_input"], g["trans_input_%d" % i])
+        assert np.array_equal(meta["trans_output"], g["trans_output_%d" % i])
+
+
+def test_warp_affine_oracle_matches_cv2():
+    """The integer restatement of cv2.warpAffine (uint8, INTER_LINEAR, BORDER_CONSTANT) vs cv2 itself:
+    scaling, rotation + shear, up-sampling with borders, negative source coordinates, 1-channel."""
+    import cv2
+    from oracle import preprocess as opre
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (90, 160, 3), dtype=np.uint8)
+    mats = [np.array([[0.6, 0, 0], [0, 0.6, 21.0]]), np.array([[0.75, 0, 0.3], [0, 0.75, 26.3]]),
+            np.array([[0.61, 0.05, -3.3], [-0.04, 0.58, 22.5]]), np.array([[1.7, 0.0, -100.5], [0.0, 1.7, -50.25]]),
+            np.array([[-0.9, 0.3, 140.0], [0.2, 1.1, -10.0]])]
+    for M in mats:
+        for ds in [(96, 96), (131, 57)]:
+            assert np.array_equal(opre.warp_affine_u8(img, M, ds), cv2.warpAffine(img, M, ds, flags=cv2.INTER_LINEAR))
+    gray = img[:, :, 0].copy()
+    assert np.array_equal(opre.warp_affine_u8(gray, mats[2], (64, 64)),
+                          cv2.warpAffine(gray, mats[2], (64, 64), flags=cv2.INTER_LINEAR))
+
+
+def test_preprocess_host_meta_matches_reference_golden(golden):
+    """Host side of the product (sgtapose_b200/preprocess.py): same matrices / meta as the reference."""
+    import types
+    from oracle.make_golden_preprocess import CASES
+    from sgtapose_b200 import preprocess as pre
+    g = golden("preprocess.npz")
+    for i, (raw, inp, _) in enumerate(CASES):
+        opt = types.SimpleNamespace(fix_res=True, fix_short=-1, input_h=inp[0], input_w=inp[1], down_ratio=4)
+        meta = pre.transform_meta(raw[0], raw[1], opt)
+        assert np.array_equal(meta["trans_input"], g["trans_input_%d" % i])
+        assert np.array_equal(meta["trans_output"], g["trans_output_%d" % i])
+        assert np.array_equal(meta["c"], g["c_%d" % i]) and float(meta["s"]) == float(g["s_%d" % i])
+        assert (meta["out_height"], meta["out_width"]) == (inp[0] // 4, inp[1] // 4)
+    with pytest.raises(Exception):
+        pre.warp_normalize(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), np.eye(2, 3), (8, 8))   # no CPU fallback
