@@ -380,13 +380,21 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
   float m = 0.f;
   bool pos = true;                                              // false on any negative or NaN element
   if ((hw & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // nine 16-byte loads in flight per thread (a whole 96x96 map per CTA) before the first use
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(bufA);
-    for (int e = tid; e < (hw >> 2); e += 256) {
-      float4 v = __ldg(s4 + e);
-      d4[e] = v;
-      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-      pos = pos && (v.x >= 0.f) && (v.y >= 0.f) && (v.z >= 0.f) && (v.w >= 0.f);
+    const int n4 = hw >> 2;
+    for (int base = tid; base < n4; base += 9 * 256) {
+      float4 v[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        v[j] = base + j * 256 < n4 ? __ldg(s4 + base + j * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        if (base + j * 256 < n4) d4[base + j * 256] = v[j];
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v[j].x), fabsf(v[j].y))), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
+        pos = pos && (v[j].x >= 0.f) && (v[j].y >= 0.f) && (v[j].z >= 0.f) && (v[j].w >= 0.f);
+      }
     }
   } else {
     for (int e = tid; e < hw; e += 256) {
@@ -487,32 +495,44 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
     const float er = exact_mode ? 0.f : (nonneg ? ERR_BOUND : 0.f);   // |v - v_ref| <= er * v + ea
     const float ea = exact_mode ? 0.f : (nonneg ? 0.f : EM);
     for (int y = warp; y < h; y += 8) {
-      const float* p = bufA + y * wp + lane;
-      for (int x = lane; x < w; x += 32, p += 32) {
-        const float v = *p;
-        const float ev = fmaf(er, v, ea);
-        if (v < BLUR_THRESH - ev) continue;                     // surely not above the threshold
-        const float nb[4] = {y > 0 ? p[-wp] : 0.f, y < h - 1 ? p[wp] : 0.f, x > 0 ? p[-1] : 0.f,
-                             x < w - 1 ? p[1] : 0.f};
-        bool sure = v > BLUR_THRESH + ev, drop = false;
+      const float* rowp = bufA + y * wp;
+      for (int x0 = lane; x0 < w; x0 += 128) {
+        // threshold test of four pixels per lane first: almost every pixel of a heat map ends here
+        float v4[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float band = ev + fmaf(er, nb[k], ea);
-          const float d = v - nb[k];
-          drop = drop || d < -band;                             // surely below a neighbour
-          sure = sure && d > band;
-        }
-        if (drop) continue;
-        if (!sure) {                                            // inside the rounding band, a tie, or NaN/Inf
-          if (exact_mode) {                                     // image_proc.py:1054-1073 on exact values
-            if (!(v > BLUR_THRESH && v >= nb[0] && v >= nb[1] && v >= nb[2] && v >= nb[3])) continue;
-          } else {
-            const int slot = atomicAdd(&s_nund, 1);
-            if (slot < UND_CAP) s_list[slot] = y * w + x;       // re-checked by the whole CTA below
-            continue;
+        for (int j = 0; j < 4; ++j) v4[j] = x0 + 32 * j < w ? rowp[x0 + 32 * j] : 0.f;
+        unsigned pass = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (x0 + 32 * j < w && !(v4[j] < BLUR_THRESH - fmaf(er, v4[j], ea))) pass |= 1u << j;
+        while (pass) {
+          const int x = x0 + 32 * (__ffs(pass) - 1);
+          pass &= pass - 1;
+          const float* p = rowp + x;
+          const float v = *p;
+          const float ev = fmaf(er, v, ea);
+          const float nb[4] = {y > 0 ? p[-wp] : 0.f, y < h - 1 ? p[wp] : 0.f, x > 0 ? p[-1] : 0.f,
+                               x < w - 1 ? p[1] : 0.f};
+          bool sure = v > BLUR_THRESH + ev, drop = false;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float band = ev + fmaf(er, nb[k], ea);
+            const float d = v - nb[k];
+            drop = drop || d < -band;                           // surely below a neighbour
+            sure = sure && d > band;
           }
+          if (drop) continue;
+          if (!sure) {                                          // inside the rounding band, a tie, or NaN/Inf
+            if (exact_mode) {                                   // image_proc.py:1054-1073 on exact values
+              if (!(v > BLUR_THRESH && v >= nb[0] && v >= nb[1] && v >= nb[2] && v >= nb[3])) continue;
+            } else {
+              const int slot = atomicAdd(&s_nund, 1);
+              if (slot < UND_CAP) s_list[slot] = y * w + x;     // re-checked by the whole CTA below
+              continue;
+            }
+          }
+          acc_list[atomicAdd(&s_nacc, 1)] = y * w + x;
         }
-        acc_list[atomicAdd(&s_nacc, 1)] = y * w + x;
       }
     }
     __syncthreads();
