@@ -351,8 +351,30 @@ __device__ __noinline__ float exact_pass2(const float* row, int x, int w, const 
   return (float)t;
 }
 
+// ---- packed float32 pairs (FFMA2, sm_100): two maps columns (pass 1) or two map rows (pass 2) per lane-op.
+// Each half is an IEEE fused multiply-add, so the results equal the scalar chains bit for bit.
+constexpr int SEG2 = 6;                     // outputs per item and half
+
+// One item of a packed pass: SEG2 outputs x 2 halves from SEG2 + 24 float2 inputs at `base + idx(i)`.
+// Input-major order keeps one input pair live; per output the taps still accumulate in order t = 0..24.
+template <bool INTERIOR>
+__device__ __forceinline__ void packed_taps(const float2* __restrict__ base, int stride, int first, int n,
+                                            const float2 (&w2)[2 * GR + 1], float2 (&a2)[SEG2]) {
+#pragma unroll
+  for (int k = 0; k < SEG2; ++k) a2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < SEG2 + 2 * GR; ++i) {
+    const int pos = INTERIOR ? first + i : refl1(first + i, n);
+    const float2 v = base[pos * stride];
+#pragma unroll
+    for (int k = 0; k < SEG2; ++k)
+      if (i - k >= 0 && i - k <= 2 * GR) a2[k] = __ffma2_rn(v, w2[i - k], a2[k]);
+  }
+}
+
 constexpr int UND_CAP = 64;     // more undecided pixels than this: the whole map is re-blurred in float64
 
+template <bool PACKED>
 __global__ void __launch_bounds__(256, 3)
 decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
                         const float* __restrict__ tracking, float* __restrict__ scores,
@@ -414,75 +436,116 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
   const float EM = ERR_BOUND * m;                               // sign-agnostic bound
   const bool nonneg = s_min_ok;                                 // x >= 0 everywhere: sum w|x| is the blur itself
 
-  // phase 1: vertical taps
-  const int nsy = (h + SEG - 1) / SEG;
-  for (int it = tid; it < nsy * w; it += 256) {
-    const int sg = it / w, x = it - sg * w, y0 = sg * SEG;
-    float in[SEG + 2 * GR];
-    if (y0 >= GR && y0 + SEG + GR <= h) {                       // interior segment: no fold
-      const float* col = bufA + (y0 - GR) * w + x;
+  if (PACKED) {
+    // h, w even and >= SEG2 + 2*GR (launcher).  Pass 1: lane = two adjacent columns (one LDS.64 of the dense
+    // map per input row); its output goes to bufB interleaved by ROW PAIR, [h/2][w|1] float2 = (row 2j, row 2j+1),
+    // so that pass 2 (lane = two adjacent rows) also reads one LDS.64 per input column.
+    float2 w2[2 * GR + 1];
 #pragma unroll
-      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = col[r * w];
-    } else if (h >= SEG + 2 * GR) {                             // first / last segments: one fold
+    for (int t = 0; t < 2 * GR + 1; ++t) w2[t] = make_float2(gf.w[t], gf.w[t]);
+    float2* tmpI = reinterpret_cast<float2*>(bufB);
+    const int wh = w >> 1, hh = h >> 1;
+    const int nsy = (h + SEG2 - 1) / SEG2;
+    for (int it = tid; it < nsy * wh; it += 256) {
+      const int sg = it / wh, x = 2 * (it - sg * wh), y0 = sg * SEG2;
+      const float2* col = reinterpret_cast<const float2*>(bufA + x);    // row stride w floats = w/2 float2
+      float2 a2[SEG2];
+      if (y0 >= GR && y0 + SEG2 + GR <= h) packed_taps<true>(col, wh, y0 - GR, h, w2, a2);
+      else packed_taps<false>(col, wh, y0 - GR, h, w2, a2);
 #pragma unroll
-      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = bufA[refl1(y0 - GR + r, h) * w + x];
-    } else {
-#pragma unroll
-      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = bufA[refl(y0 - GR + r, h) * w + x];
+      for (int k = 0; k < SEG2; k += 2) {
+        if (y0 + k < h) {
+          float2* o = tmpI + ((y0 + k) >> 1) * wp + x;
+          o[0] = make_float2(a2[k].x, a2[k + 1].x);
+          o[1] = make_float2(a2[k].y, a2[k + 1].y);
+        }
+      }
     }
-    float a[SEG];                                               // SEG independent chains: tap-major order
+    __syncthreads();
+    const int nsx = (w + SEG2 - 1) / SEG2;
+    for (int it = tid; it < nsx * hh; it += 256) {
+      const int sg = it / hh, yp = it - sg * hh, x0 = sg * SEG2;
+      const float2* row = tmpI + yp * wp;
+      float2 a2[SEG2];
+      if (x0 >= GR && x0 + SEG2 + GR <= w) packed_taps<true>(row, 1, x0 - GR, w, w2, a2);
+      else packed_taps<false>(row, 1, x0 - GR, w, w2, a2);
+      float* o0 = bufA + (2 * yp) * wp + x0;
 #pragma unroll
-    for (int k = 0; k < SEG; ++k) a[k] = in[k] * gf.w[0];
-#pragma unroll
-    for (int t = 1; t < 2 * GR + 1; ++t)
-#pragma unroll
-      for (int k = 0; k < SEG; ++k) a[k] = fmaf(in[k + t], gf.w[t], a[k]);
-    float* ocol = bufB + y0 * wp + x;
-    if (y0 + SEG <= h) {
-#pragma unroll
-      for (int k = 0; k < SEG; ++k) ocol[k * wp] = a[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < SEG; ++k)
-        if (y0 + k < h) ocol[k * wp] = a[k];
+      for (int k = 0; k < SEG2; ++k)
+        if (x0 + k < w) { o0[k] = a2[k].x; o0[wp + k] = a2[k].y; }
     }
-  }
-  __syncthreads();
+    __syncthreads();
+  } else {
+    // phase 1: vertical taps
+    const int nsy = (h + SEG - 1) / SEG;
+    for (int it = tid; it < nsy * w; it += 256) {
+      const int sg = it / w, x = it - sg * w, y0 = sg * SEG;
+      float in[SEG + 2 * GR];
+      if (y0 >= GR && y0 + SEG + GR <= h) {                       // interior segment: no fold
+        const float* col = bufA + (y0 - GR) * w + x;
+  #pragma unroll
+        for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = col[r * w];
+      } else if (h >= SEG + 2 * GR) {                             // first / last segments: one fold
+  #pragma unroll
+        for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = bufA[refl1(y0 - GR + r, h) * w + x];
+      } else {
+  #pragma unroll
+        for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = bufA[refl(y0 - GR + r, h) * w + x];
+      }
+      float a[SEG];                                               // SEG independent chains: tap-major order
+  #pragma unroll
+      for (int k = 0; k < SEG; ++k) a[k] = in[k] * gf.w[0];
+  #pragma unroll
+      for (int t = 1; t < 2 * GR + 1; ++t)
+  #pragma unroll
+        for (int k = 0; k < SEG; ++k) a[k] = fmaf(in[k + t], gf.w[t], a[k]);
+      float* ocol = bufB + y0 * wp + x;
+      if (y0 + SEG <= h) {
+  #pragma unroll
+        for (int k = 0; k < SEG; ++k) ocol[k * wp] = a[k];
+      } else {
+  #pragma unroll
+        for (int k = 0; k < SEG; ++k)
+          if (y0 + k < h) ocol[k * wp] = a[k];
+      }
+    }
+    __syncthreads();
 
-  // phase 2: horizontal taps
-  const int nsx = (w + SEG - 1) / SEG;
-  for (int it = tid; it < nsx * h; it += 256) {
-    const int sg = it / h, y = it - sg * h, x0 = sg * SEG;
-    const float* row = bufB + y * wp;
-    float in[SEG + 2 * GR];
-    if (x0 >= GR && x0 + SEG + GR <= w) {
-#pragma unroll
-      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[x0 - GR + r];
-    } else if (w >= SEG + 2 * GR) {
-#pragma unroll
-      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[refl1(x0 - GR + r, w)];
-    } else {
-#pragma unroll
-      for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[refl(x0 - GR + r, w)];
+    // phase 2: horizontal taps
+    const int nsx = (w + SEG - 1) / SEG;
+    for (int it = tid; it < nsx * h; it += 256) {
+      const int sg = it / h, y = it - sg * h, x0 = sg * SEG;
+      const float* row = bufB + y * wp;
+      float in[SEG + 2 * GR];
+      if (x0 >= GR && x0 + SEG + GR <= w) {
+  #pragma unroll
+        for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[x0 - GR + r];
+      } else if (w >= SEG + 2 * GR) {
+  #pragma unroll
+        for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[refl1(x0 - GR + r, w)];
+      } else {
+  #pragma unroll
+        for (int r = 0; r < SEG + 2 * GR; ++r) in[r] = row[refl(x0 - GR + r, w)];
+      }
+      float* orow = bufA + y * wp + x0;
+      float a[SEG];
+  #pragma unroll
+      for (int k = 0; k < SEG; ++k) a[k] = in[k] * gf.w[0];
+  #pragma unroll
+      for (int t = 1; t < 2 * GR + 1; ++t)
+  #pragma unroll
+        for (int k = 0; k < SEG; ++k) a[k] = fmaf(in[k + t], gf.w[t], a[k]);
+      if (x0 + SEG <= w) {
+  #pragma unroll
+        for (int k = 0; k < SEG; ++k) orow[k] = a[k];
+      } else {
+  #pragma unroll
+        for (int k = 0; k < SEG; ++k)
+          if (x0 + k < w) orow[k] = a[k];
+      }
     }
-    float* orow = bufA + y * wp + x0;
-    float a[SEG];
-#pragma unroll
-    for (int k = 0; k < SEG; ++k) a[k] = in[k] * gf.w[0];
-#pragma unroll
-    for (int t = 1; t < 2 * GR + 1; ++t)
-#pragma unroll
-      for (int k = 0; k < SEG; ++k) a[k] = fmaf(in[k + t], gf.w[t], a[k]);
-    if (x0 + SEG <= w) {
-#pragma unroll
-      for (int k = 0; k < SEG; ++k) orow[k] = a[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < SEG; ++k)
-        if (x0 + k < w) orow[k] = a[k];
-    }
+    __syncthreads();
   }
-  __syncthreads();
 
   // phase 3: scan.  Round 0 tests the float32 blur with margins: accepted peaks and undecided pixels go to
   // shared-memory lists (the loop itself stays light); if more than UND_CAP pixels fall inside the rounding
@@ -804,10 +867,12 @@ extern "C" int sgta_decode_peaks(const void* hm, const void* reg, const void* tr
   plane = (plane + 3) & ~(size_t)3;
   const size_t smem = 2 * plane * sizeof(float);
   if (smem <= 226 * 1024) {
-    cudaFuncSetAttribute(decode_peaks_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(decode_peaks_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-    decode_peaks_f32_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>(
+    // packed pairs need even sizes (8-byte aligned pair loads) and single-fold reflection
+    const bool packed = !(h & 1) && !(w & 1) && h >= SEG2 + 2 * GR && w >= SEG2 + 2 * GR;
+    auto kern = packed ? decode_peaks_f32_kernel<true> : decode_peaks_f32_kernel<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<B * C, 256, smem, (cudaStream_t)stream>>>(
         (const float*)hm, (const float*)reg, (const float*)tracking, (float*)scores, (long long*)inds,
         (long long*)xs, (long long*)ys, (float*)cts_wreg, (float*)trk, gw, gf, C, h, w, (int)plane);
     return check_launch("decode_peaks_f32_kernel");
