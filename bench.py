@@ -259,7 +259,7 @@ def run_ours(args):
     extra = {}
     if rank == 0 and world == 1 and args.engine != "eager" and not args.no_extras:
         extra["roofline_decode"] = decode_roofline(dev)
-        extra["pipeline"] = clip_pipeline(eng, dev, args.clip_frames)
+        extra["pipeline"] = clip_pipeline(eng, dev, args.clip_frames, sd)
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -346,7 +346,7 @@ def decode_roofline(dev, B=1024):
                     "bit-exact float64 scipy restatement (the all-float64 kernel is timed beside it)"}
 
 
-def clip_pipeline(eng, dev, frames):
+def clip_pipeline(eng, dev, frames, sd=None):
     """BASELINE configs[3]-style pipeline on the bench batch: lock-step clips, device prior rendering +
     network + decode, host PnP (cv2) per clip between frames.  Synthetic detections (exact projections
     + 0.5 px noise) are planted before every step so that the host PnP leg runs for every clip (random-init
@@ -379,11 +379,54 @@ def clip_pipeline(eng, dev, frames):
         det.step(imgs[f & 1], x3d(f - 1), x3d(f))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"frames_per_s": B * frames / dt, "frames": frames, "clips": B, "ms_per_step": dt / frames * 1e3,
-            "host_pnp_render_ms_per_step": det.timing["host_pnp"] / frames * 1e3,
-            "host_post_ms_per_step": det.timing["host_post"] / frames * 1e3,
-            "input": "raw uint8 %dx%d frames, device pre-processing" % (det.raw_w, det.raw_h),
-            "h2d_bytes_per_step": imgs[0].numel() + 2 * 2 * B * 7 * 2 * 8, "d2h_bytes_per_step": B * 7 * 3 * 4}
+    res = {"frames_per_s": B * frames / dt, "frames": frames, "clips": B, "ms_per_step": dt / frames * 1e3,
+           "host_pnp_render_ms_per_step": det.timing["host_pnp"] / frames * 1e3,
+           "host_post_ms_per_step": det.timing["host_post"] / frames * 1e3,
+           "input": "raw uint8 %dx%d frames, device pre-processing" % (det.raw_w, det.raw_h),
+           "h2d_bytes_per_step": imgs[0].numel() + 2 * 2 * B * 7 * 2 * 8, "d2h_bytes_per_step": B * 7 * 3 * 4}
+    if sd is not None and B % 2 == 0:
+        # the same B clips as two groups of B/2, and 2B clips as two groups of B (the bench batch per group)
+        res["skewed_2_groups_half_batch"] = clip_groups_pipeline(sd, eng, B // 2, frames, rng)
+        res["skewed_2_groups_full_batch"] = clip_groups_pipeline(sd, eng, B, frames, rng)
+    return res
+
+
+def clip_groups_pipeline(sd, eng, per_group, frames, rng):
+    """Two lock-step groups of `per_group` clips (one engine each) run skewed
+    (sgtapose_b200/detector.py::ClipGroups): the host PnP of one group runs under the device work of the other."""
+    import numpy as np
+    from sgtapose_b200 import detector, engine
+    B = 2 * per_group
+    workers = min(16, os.cpu_count() or 1)
+    engs = [eng if per_group == eng.B and i == 0 else
+            engine.InferenceEngine(sd, eng.opt, batch=per_group, size=eng.S, mode=eng.mode, device=eng.dev, fuse_sigmoid=True)
+            for i in range(2)]
+    groups = detector.ClipGroups([detector.LockstepDetector(e, workers=workers) for e in engs])
+    K = groups.dets[0].K
+    raw_h, raw_w = groups.dets[0].raw_h, groups.dets[0].raw_w
+    base = rng.uniform([-0.35, -0.2, 1.2], [0.35, 0.2, 1.8], size=(B, 7, 3))
+    imgs = [torch.from_numpy(rng.integers(0, 256, (B, raw_h, raw_w, 3), dtype=np.uint8)).pin_memory() for f in range(2)]
+
+    def x3d(f):
+        return base + 0.004 * f
+
+    def plant(g, f, d):
+        if d.frame == 0:
+            return
+        p = np.einsum("ij,bkj->bki", K, x3d(f - 1)[groups.offsets[g]:groups.offsets[g + 1]])
+        d.detected_kps = p[:, :, :2] / p[:, :, 2:] + rng.normal(0, 0.5, size=(d.B, 7, 2))
+
+    groups.run(3, lambda f: imgs[f & 1], x3d, before_begin=plant)       # warm-up (graphs, PnP path)
+    for d in groups.dets:
+        d.timing = {"host_pnp": 0.0, "host_post": 0.0, "steps": 0}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    groups.run(frames, lambda f: imgs[f & 1], x3d, before_begin=plant)   # frame 0 of this run re-uses the kept state
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    host = sum(d.timing["host_pnp"] + d.timing["host_post"] for d in groups.dets)
+    return {"frames_per_s": B * frames / dt, "ms_per_step": dt / frames * 1e3, "groups": 2, "clips_per_group": per_group,
+            "clips": B, "host_ms_per_step_all_groups": host / frames * 1e3}
 
 
 def time_dcn_kernels(fn):

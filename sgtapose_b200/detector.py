@@ -112,6 +112,8 @@ class LockstepDetector:
         self._d_in = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64, device=dev)
         self._d_out = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64, device=dev)
         self._res = torch.zeros(self.B, self.n_kp, 3, dtype=torch.float32).pin_memory()
+        self._done = torch.cuda.Event()
+        self._begun = False
         self.reset()
 
     def reset(self):
@@ -147,6 +149,14 @@ class LockstepDetector:
         host or device) that are pre-processed on the device.  x3d_prev / x3d_next: [B,n_kp,3] keypoint
         positions w.r.t. the camera in the previous / this frame (ignored at frame 0).
         Returns {'kps_raw' [B,n_kp,2] float64 (MISSING = not detected), 'scores' [B,n_kp]}."""
+        self.begin(images, x3d_prev, x3d_next)
+        return self.finish()
+
+    def begin(self, images, x3d_prev=None, x3d_next=None):
+        """First half of `step`: the host PnP of every clip, then everything the device has to do for this
+        frame is ENQUEUED (uploads, pre-processing, prior maps, network, decode, result download) and the
+        call returns.  `finish` waits for it.  Between the two the host is free -- `ClipGroups` uses that to
+        run another group's PnP under this group's device work."""
         eng, inp = self.eng, self.eng.inp
         t0 = time.perf_counter()
         if isinstance(images, np.ndarray):
@@ -191,14 +201,73 @@ class LockstepDetector:
         packed = torch.cat([dets["scores"].view(self.B, self.n_kp, 1),
                             dets["cts_wreg"].view(self.B, self.n_kp, 2)], dim=2)
         self._res.copy_(packed, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        self._done.record(torch.cuda.current_stream(eng.dev))
+        self.timing["host_pnp"] += t1 - t0
+        self._begun = True
+
+    def finish(self):
+        """Second half of `step`: wait for the frame enqueued by `begin`, post-process on the host."""
+        if not self._begun:
+            raise RuntimeError("finish() without begin()")
+        self._begun = False
+        self._done.synchronize()
         t2 = time.perf_counter()
         r = self._res.numpy()
         scores = r[:, :, 0].copy()
         self.detected_kps = self._post(scores, r[:, :, 1:3])
         t3 = time.perf_counter()
-        self.timing["host_pnp"] += t1 - t0
         self.timing["host_post"] += t3 - t2
         self.timing["steps"] += 1
         self.frame += 1
         return {"kps_raw": self.detected_kps.copy(), "scores": scores}
+
+
+class ClipGroups:
+    """G lock-step groups of clips, one engine each, run SKEWED: while the device works on group g's frame,
+    the host solves the PnP of group g+1 (and post-processes group g-1).  Clips are independent
+    (inference.py:201-205 builds a fresh detector per clip), so splitting the batch changes nothing that is
+    computed -- only the host work (north_star keeps LM/PnP on the host) stops serialising with the device:
+
+        begin(A,f) begin(B,f) | finish(A,f) begin(A,f+1) | finish(B,f) begin(B,f+1) | ...
+
+    `run` drives that schedule for a whole sequence."""
+
+    def __init__(self, detectors):
+        self.dets = list(detectors)
+        self.B = sum(d.B for d in self.dets)
+        self.offsets = np.cumsum([0] + [d.B for d in self.dets])
+
+    def reset(self):
+        for d in self.dets:
+            d.reset()
+
+    def _slice(self, a, g):
+        return None if a is None else a[self.offsets[g]:self.offsets[g + 1]]
+
+    def run(self, n_frames, images_fn, x3d_fn=None, before_begin=None):
+        """images_fn(f) -> frames of ALL clips for frame f ([B,...] uint8 raw or float32 network inputs);
+        x3d_fn(f) -> [B,n_kp,3] keypoint positions w.r.t. the camera in frame f.
+        before_begin(g, f, det): optional hook called right before group g's begin of frame f (tests and the
+        bench plant detections there).  Returns per-frame {'kps_raw' [B,n_kp,2], 'scores' [B,n_kp]}."""
+        G = len(self.dets)
+        out = [dict() for _ in range(n_frames)]
+
+        def begin(g, f):
+            d = self.dets[g]
+            if before_begin is not None:
+                before_begin(g, f, d)
+            prev = self._slice(x3d_fn(f - 1), g) if (x3d_fn is not None and d.frame > 0) else None
+            nxt = self._slice(x3d_fn(f), g) if (x3d_fn is not None and d.frame > 0) else None
+            d.begin(self._slice(images_fn(f), g), prev, nxt)
+
+        def finish(g, f):
+            out[f][g] = self.dets[g].finish()
+
+        for g in range(G):
+            begin(g, 0)
+        for f in range(n_frames):
+            for g in range(G):
+                finish(g, f)
+                if f + 1 < n_frames:
+                    begin(g, f + 1)
+        return [{k: np.concatenate([fr[g][k] for g in range(G)]) for k in ("kps_raw", "scores")} for fr in out]

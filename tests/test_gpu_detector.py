@@ -105,3 +105,47 @@ def test_step_accepts_raw_uint8_frames(det):
     assert np.array_equal(out_raw["kps_raw"], out_f32["kps_raw"]) and np.array_equal(out_raw["scores"], out_f32["scores"])
     with pytest.raises(ValueError):
         det.step(frames[:, :100])
+
+
+def test_clip_groups_skewed_schedule_equals_group_by_group(det):
+    """Two groups (2 + 1 clips, one engine each) run skewed == the same two detectors stepped one after the
+    other: the schedule only re-orders host work, every frame's detections are identical, with the PnP branch
+    active from frame 1 on.  (Engines of different batch size are NOT compared bit-wise: reduction splits in
+    the token kernels depend on the token count, and the synthetic weights amplify 1-ulp differences.)"""
+    from sgtapose_b200 import config, detector, engine, networks, synth
+    m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), config.default_opt())
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=C.GOLDEN_SEED)
+    engs = [engine.InferenceEngine(sd, config.default_opt(), batch=b, size=S, mode="fp32", device=DEV, fuse_sigmoid=True)
+            for b in (2, 1)]
+    groups = detector.ClipGroups([detector.LockstepDetector(e, workers=2) for e in engs])
+    assert groups.B == B
+    n_frames = 4
+    x3d = [_scene(np.random.default_rng(7), B, f) for f in range(n_frames)]
+    imgs = [synth.synthetic_inputs(B, S, seed=200 + f, frame=1)[0].pin_memory() for f in range(n_frames)]
+    proj = np.einsum("ij,bkj->bki", det.K, x3d[0])
+    planted = proj[:, :, :2] / proj[:, :, 2:]
+    planted[1, [2, 5]] = odet.MISSING
+    off = groups.offsets
+
+    # reference run: each group on its own, plain step()
+    want = [dict() for _ in range(n_frames)]
+    for g, d in enumerate(groups.dets):
+        d.reset()
+        for f in range(n_frames):
+            if f == 1:
+                d.detected_kps = planted[off[g]:off[g + 1]].copy()
+            sl = slice(off[g], off[g + 1])
+            want[f][g] = d.step(imgs[f][sl], x3d[f - 1][sl] if f else None, x3d[f][sl] if f else None)
+
+    def plant(g, f, d):
+        if f == 1:
+            d.detected_kps = planted[off[g]:off[g + 1]].copy()
+
+    groups.reset()
+    got = groups.run(n_frames, lambda f: imgs[f], lambda f: x3d[f], before_begin=plant)
+    for f in range(n_frames):
+        for k in ("kps_raw", "scores"):
+            assert np.array_equal(got[f][k], np.concatenate([want[f][0][k], want[f][1][k]])), (f, k)
+    assert all(d.frame == n_frames for d in groups.dets)
+    with pytest.raises(RuntimeError):
+        groups.dets[0].finish()                            # finish() without begin()

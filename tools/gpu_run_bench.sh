@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench_fp32.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --profile-pass --no-cpu-baseline > gpurun_out/launches.log 2>&1; echo "ncu rc=$?"
-python tools/launch_summary.py gpurun_out/launches.csv 200 > gpurun_out/launch_summary.txt 2>&1; head -30 gpurun_out/launch_summary.txt
+timeout 400 python -m pytest tests/test_gpu_detector.py -x -q > gpurun_out/t_detector.log 2>&1; echo "detector tests rc=$?"; tail -15 gpurun_out/t_detector.log
+timeout 600 python bench.py > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err; echo "bench rc=$?"; tail -c 1800 gpurun_out/bench_fp32.json; tail -5 gpurun_out/bench_fp32.err
