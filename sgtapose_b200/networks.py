@@ -366,6 +366,13 @@ class DLA_PlanAWindow_l3new(nn.Module):
         return [y[-1]], pre_ids_0, cur_ids_0
 
     def forward(self, x, pre_img=None, pre_hm=None, repro_hm=None, pre_hm_cls=None, repro_hm_cls=None):
+        # the plain convolutions of this module tree are cuDNN calls, which default to TF32 (1e-3 per op):
+        # keep them in fp32 so the tree meets the same 1e-3 end-to-end bound as the compiled engine
+        cd = torch.backends.cudnn
+        with cd.flags(enabled=cd.enabled, benchmark=cd.benchmark, deterministic=cd.deterministic, allow_tf32=False):
+            return self._forward(x, pre_img, pre_hm, repro_hm, pre_hm_cls, repro_hm_cls)
+
+    def _forward(self, x, pre_img, pre_hm, repro_hm, pre_hm_cls, repro_hm_cls):
         if all(t is None for t in (pre_img, pre_hm, repro_hm, pre_hm_cls, repro_hm_cls)):
             feats = self.img2feats(x)
         else:
