@@ -317,7 +317,9 @@ decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
 //            neighbours, lists of accepted / undecided pixels; centroids spread over the CTA, block top-2,
 //            emit.  (NaN/Inf inputs, more than 256 hot items and the float64 round scan every pixel instead.)
 // Measured and rejected: a per-pixel candidate bit mask set by phase 2 (+2.6 k instructions there, scan no
-// shorter: 0.36 ms vs 0.325 ms per 1024 frames).
+// shorter: 0.36 ms vs 0.325 ms per 1024 frames); persistent CTAs with a third plane that prefetches the next
+// map by cp.async (2 CTAs/SM instead of 3: 0.37 ms vs 0.30 ms -- resident warps matter more than the
+// phase-0 DRAM latency).
 // ---------------------------------------------------------------------------------------
 struct GaussWF { float w[25]; };
 constexpr int SEG = 12;
