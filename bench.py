@@ -259,6 +259,7 @@ def run_ours(args):
     extra = {}
     if rank == 0 and world == 1 and args.engine != "eager" and not args.no_extras:
         extra["roofline_decode"] = decode_roofline(dev)
+        extra["roofline_preprocess"] = preprocess_roofline(dev)
         extra["pipeline"] = clip_pipeline(eng, dev, args.clip_frames, sd)
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -344,6 +345,36 @@ def decode_roofline(dev, B=1024):
             "float64_rechecked_pixels_per_launch": rechecks,
             "note": "float32 blur with a rigorous rounding band; pixels inside the band are re-evaluated with the "
                     "bit-exact float64 scipy restatement (the all-float64 kernel is timed beside it)"}
+
+
+def preprocess_roofline(dev, B=256):
+    """Device pre-processing alone (SURVEY.md 8f rank 2): B raw 640x360 uint8 frames -> [B,3,384,384] fp32 per launch;
+    algorithmic bytes = raw frame read once + network input written once; CUDA events, median of 5."""
+    import numpy as np
+    from sgtapose_b200 import config, preprocess
+    rng = np.random.default_rng(317)
+    frames = torch.from_numpy(rng.integers(0, 256, (B, 360, 640, 3), dtype=np.uint8)).to(dev)
+    opt = config.default_opt(fix_res=True, fix_short=-1, input_h=S, input_w=S, down_ratio=4)
+    meta = preprocess.transform_meta(360, 640, opt)
+    out = torch.empty(B, 3, S, S, device=dev)
+    for _ in range(3):
+        preprocess.warp_normalize(frames, meta["trans_input"], (S, S), out=out)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        preprocess.warp_normalize(frames, meta["trans_input"], (S, S), out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[2]
+    peaks, which = _peaks()
+    nbytes = frames.numel() + out.numel() * 4
+    gbs = nbytes / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "preprocess_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": gbs / peaks["hbm_gbs"], "traffic": None, "frames_per_launch": B, "ms": ms,
+            "frames_per_s": B / (ms / 1e3), "peak_source": which}
 
 
 def clip_pipeline(eng, dev, frames, sd=None):
