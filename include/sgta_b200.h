@@ -330,6 +330,20 @@ int sgta_render_priors(const void* centres_in, const void* centres_out, void* hm
 int sgta_preprocess(const void* img_u8, void* out, void* out_u8, const double* trans, int n_trans,
                     const float* mean3, const float* std3, int B, int h, int w, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Host-side pose refinement (no device work): the `LM` entry of the reference's
+ * binary-only rf_tools/libtestso_final.so, bound at sgtapose/rf_tools/LM.py:10 and called from
+ * `register_GN_C` (:256-266).  All pointers are HOST memory.
+ *   value_init [7]  qw qx qy qz tx ty tz (start: the PnP pose)
+ *   x2d [n,2] detected keypoints (pixels), x3d [n,3] keypoints in the robot frame
+ *   weights [2n+2]  per-coordinate weights, last two = the unit-quaternion constraint weights (1e8)
+ *   camera [9]      row-major 3x3 intrinsics;   ans [7] refined qw qx qy qz tx ty tz
+ * Minimises sum_k F_k^2 with F as in LM.py `fun` (:128-156).  `LM` is the same entry under the
+ * reference's own symbol name and argument list (void return; NaN in `ans` on failure). */
+int sgta_lm_refine(const double* value_init, const double* x2d, const double* x3d, const double* weights,
+                   const double* camera, double* ans, int num_points);
+void LM(double* value_init, double* x2d, double* x3d, double* weights, double* camera, double* ans, int num_points);
+
 #ifdef __cplusplus
 }
 #endif

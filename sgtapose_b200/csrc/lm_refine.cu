@@ -1,0 +1,165 @@
+// Pose refinement on the HOST (north_star: "the Levenberg-Marquardt/PnP solve in
+// rf_tools stays on the host").  No device code in this file.
+//
+// Reference: sgtapose/rf_tools/LM.py -- `register_GN_C` (:256-266) hands seven start values
+// (qw qx qy qz tx ty tz), n 2-D / 3-D correspondences, 2n+2 weights and the 3x3 camera matrix to
+// `LM(...)` of the binary-only `libtestso_final.so` (:10; no source in the tree).  The file's own Python
+// twin states the algorithm: `fun` (:128-156) builds the 2n+1 "residuals"
+//     F[2i]   = wx_i^2 (x2d_i - u_i)^2,   F[2i+1] = wy_i^2 (y2d_i - v_i)^2,
+//     F[2n]   = 1e8 (|q|^2 - 1)^2 + 1e8 (|q|^2 - 1)^2         (unit-quaternion constraint)
+// with (u, v) the pinhole projection of q X q* + t for the UN-normalised quaternion q, `dfun` (:161-217)
+// their Jacobian, and `GN` (:220-232) iterates  value -= (J^T J + 1e-4 I)^-1 J^T F  until the step's
+// 1-norm is <= 1e-4 or 200 iterations.  Probed against the binary (oracle/make_golden_lm.py): the .so IS
+// that iteration in float64 -- without the twin's float32 cast of J^T J, and WITH the twin's Jacobian as
+// written, whose d F_v / d qz entry (:208) repeats the d F_v / d qy expression (:207).  Both are restated
+// here (the Jacobian from the quaternion product rather than from the generated expressions); the result
+// agrees with the .so to 1e-9 .. 1e-16 on converging problems (tests/golden/lm.npz).  The iteration stops
+// on step size, not at the minimum, so a "better" solver would NOT be a drop-in: poses must match the
+// reference's to 1 mm / 0.1 deg.
+//
+// `LM` is exported under the reference's symbol name and argument list, so LM.py:10 can load this
+// library instead of libtestso_final.so unchanged.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sgta {
+
+constexpr int LM_P = 7;
+
+// F [2n+1], J [(2n+1) x 7] row-major (J may be null)
+static void lm_eval(const double* v, const double* x2d, const double* x3d, const double* w, const double* K, int n,
+                    double* F, double* J) {
+  const double qw = v[0], qx = v[1], qy = v[2], qz = v[3], tx = v[4], ty = v[5], tz = v[6];
+  const double fx = K[0], cx = K[2], fy = K[4], cy = K[5];
+  for (int i = 0; i < n; ++i) {
+    const double x = x3d[3 * i], y = x3d[3 * i + 1], z = x3d[3 * i + 2];
+    // q * (0, X) = (d, a, b, c);  P = vector part of (q * (0, X)) * conj(q) + t
+    const double a = qw * x + qy * z - qz * y, b = qw * y - qx * z + qz * x, c = qw * z + qx * y - qy * x;
+    const double d = -qx * x - qy * y - qz * z;
+    const double Px = qw * a - qx * d + qy * c - qz * b + tx;
+    const double Py = qw * b - qx * c - qy * d + qz * a + ty;
+    const double Pz = qw * c + qx * b - qy * a - qz * d + tz;
+    const double u = (cx * Pz + fx * Px) / Pz, vv = (cy * Pz + fy * Py) / Pz;
+    const double wx2 = w[2 * i] * w[2 * i], wy2 = w[2 * i + 1] * w[2 * i + 1];
+    const double ru = x2d[2 * i] - u, rv = x2d[2 * i + 1] - vv;
+    F[2 * i] = wx2 * ru * ru;
+    F[2 * i + 1] = wy2 * rv * rv;
+    if (J) {
+      // dP/dq (columns qw qx qy qz), from the product rule on the expressions above
+      const double dPx[4] = {2 * a, -2 * d, 2 * c, -2 * b};
+      const double dPy[4] = {2 * b, -2 * c, -2 * d, 2 * a};
+      const double dPz[4] = {2 * c, 2 * b, -2 * a, -2 * d};
+      double* ju = J + (size_t)(2 * i) * LM_P;
+      double* jv = ju + LM_P;
+      const double iz = 1.0 / Pz, iz2 = iz * iz;
+      for (int k = 0; k < 4; ++k) {
+        const int kv = k == 3 ? 2 : k;                    // LM.py:208 == :207: the qz column of the v rows is the qy one
+        const double du = fx * (dPx[k] * Pz - Px * dPz[k]) * iz2;
+        const double dv = fy * (dPy[kv] * Pz - Py * dPz[kv]) * iz2;
+        ju[k] = -2 * wx2 * ru * du;
+        jv[k] = -2 * wy2 * rv * dv;
+      }
+      ju[4] = -2 * wx2 * ru * fx * iz; ju[5] = 0; ju[6] = -2 * wx2 * ru * (-fx * Px * iz2);
+      jv[4] = 0; jv[5] = -2 * wy2 * rv * fy * iz; jv[6] = -2 * wy2 * rv * (-fy * Py * iz2);
+    }
+  }
+  const double s = qw * qw + qx * qx + qy * qy + qz * qz - 1.0;
+  const double wc = w[2 * n] + w[2 * n + 1];              // 1e8 + 1e8 at every call site of the reference
+  F[2 * n] = wc * s * s;
+  if (J) {
+    double* jc = J + (size_t)(2 * n) * LM_P;
+    jc[0] = 2 * wc * s * 2 * qw; jc[1] = 2 * wc * s * 2 * qx; jc[2] = 2 * wc * s * 2 * qy; jc[3] = 2 * wc * s * 2 * qz;
+    jc[4] = jc[5] = jc[6] = 0;
+  }
+}
+
+// A x = b for a symmetric positive definite 7x7 (Gaussian elimination with partial pivoting); false if singular
+static bool solve7(double A[LM_P][LM_P], double* b) {
+  for (int c = 0; c < LM_P; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < LM_P; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    if (!(fabs(A[piv][c]) > 0.0) || !isfinite(A[piv][c])) return false;
+    if (piv != c) {
+      for (int k = 0; k < LM_P; ++k) { const double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+      const double t = b[c]; b[c] = b[piv]; b[piv] = t;
+    }
+    for (int r = c + 1; r < LM_P; ++r) {
+      const double f = A[r][c] / A[c][c];
+      for (int k = c; k < LM_P; ++k) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = LM_P - 1; r >= 0; --r) {
+    double s = b[r];
+    for (int k = r + 1; k < LM_P; ++k) s -= A[r][k] * b[k];
+    b[r] = s / A[r][r];
+  }
+  return true;
+}
+
+// GN (LM.py:220-232) in float64
+static int lm_solve(const double* v0, const double* x2d, const double* x3d, const double* w, const double* K, double* ans,
+                    int n) {
+  constexpr int MAXN = 64;
+  if (n <= 0 || n > MAXN) return SGTA_EINVAL;
+  const int m = 2 * n + 1;
+  double F[2 * MAXN + 1], J[(2 * MAXN + 1) * LM_P];
+  double v[LM_P];
+  memcpy(v, v0, sizeof(v));
+  double step = 7 * 100.0;                                  // delta = ones * 100
+  for (int it = 0; step > 1e-4 && it < 200; ++it) {
+    lm_eval(v, x2d, x3d, w, K, n, F, J);
+    double A[LM_P][LM_P], g[LM_P];
+    for (int a = 0; a < LM_P; ++a) {
+      g[a] = 0;
+      for (int k = 0; k < m; ++k) g[a] += J[k * LM_P + a] * F[k];
+      for (int b = a; b < LM_P; ++b) {
+        double s = 0;
+        for (int k = 0; k < m; ++k) s += J[k * LM_P + a] * J[k * LM_P + b];
+        A[a][b] = A[b][a] = s;
+      }
+      A[a][a] += 1e-4;
+    }
+    if (!solve7(A, g)) {                                    // the reference's inverse would produce NaN / Inf here
+      for (int a = 0; a < LM_P; ++a) v[a] = NAN;
+      break;
+    }
+    step = 0;
+    for (int a = 0; a < LM_P; ++a) { v[a] -= g[a]; step += fabs(g[a]); }
+    if (!(step == step)) break;                             // NaN: np.sum(abs(delta)) > 1e-4 is False
+  }
+  // Defined behaviour where the reference's iteration is chaotic: on some badly started problems the .so ends
+  // in NaN / Inf (and its caller keeps the PnP pose, analysis.py:206-210) while 1e-16 differences in the 7x7
+  // solve can send this iteration to a finite mirror pose instead.  A pose that puts a keypoint behind the
+  // camera is reported as NaN, i.e. through the caller's existing fall-back.
+  bool bad = false;
+  for (int a = 0; a < LM_P; ++a) bad = bad || !isfinite(v[a]);
+  for (int i = 0; i < n && !bad; ++i) {
+    const double x = x3d[3 * i], y = x3d[3 * i + 1], z = x3d[3 * i + 2];
+    const double a = v[0] * x + v[2] * z - v[3] * y, b = v[0] * y - v[1] * z + v[3] * x, c = v[0] * z + v[1] * y - v[2] * x;
+    const double d = -v[1] * x - v[2] * y - v[3] * z;
+    bad = !(v[0] * c + v[1] * b - v[2] * a - v[3] * d + v[6] > 0.0);
+  }
+  for (int a = 0; a < LM_P; ++a) ans[a] = bad ? NAN : v[a];
+  return SGTA_OK;
+}
+
+}  // namespace sgta
+
+using namespace sgta;
+
+extern "C" int sgta_lm_refine(const double* value_init, const double* x2d, const double* x3d, const double* weights,
+                              const double* camera, double* ans, int num_points) {
+  SGTA_REQUIRE(value_init && x2d && x3d && weights && camera && ans, "sgta_lm_refine: null pointer");
+  SGTA_REQUIRE(num_points > 0 && num_points <= 64, "sgta_lm_refine: 1..64 correspondences (got %d)", num_points);
+  return lm_solve(value_init, x2d, x3d, weights, camera, ans, num_points);
+}
+
+// the symbol rf_tools/LM.py binds (`so.LM(value_init_l, x2d_input, x3d_input, weightl, cameral, ans, num_points)`)
+extern "C" void LM(double* value_init, double* x2d, double* x3d, double* weights, double* camera, double* ans,
+                   int num_points) {
+  if (sgta_lm_refine(value_init, x2d, x3d, weights, camera, ans, num_points) != SGTA_OK)
+    for (int i = 0; i < 7; ++i) ans[i] = NAN;             // the caller falls back to the PnP pose on NaN (analysis.py:208)
+}

@@ -25,6 +25,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "missing export: " + s
     assert set(syms) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert hasattr(lib, "LM"), "the reference's rf_tools entry name (LM.py:10) must be exported too"
     assert lib.sgta_abi_version() == 1
 
 
