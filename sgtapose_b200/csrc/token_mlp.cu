@@ -59,9 +59,9 @@ __device__ __forceinline__ void allreduce_vec(float (&v)[C]) {
 template <int C>
 __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int n, int tid) {
   constexpr int V = C / 4;
-  constexpr int TM_THREADS = TmThreads<C>::value;
+  const int nthreads = blockDim.x;
   const float4* s4 = reinterpret_cast<const float4*>(src);
-  for (int i = tid; i < n * V; i += TM_THREADS) {
+  for (int i = tid; i < n * V; i += nthreads) {
     const int r = i / V, v = i - r * V;
     *reinterpret_cast<float4*>(dst + (size_t)r * (C + 4) + 4 * v) = __ldg(s4 + i);
   }
@@ -70,9 +70,8 @@ __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__
 // smem: [max(hid, jh) * CS] + [jh * CS] floats, CS = C + 4
 template <int C, int LPT>
 __global__ void __launch_bounds__(TmThreads<C>::value, 1) token_mlp_kernel(const TokenMlpP p) {
-  constexpr int TM_THREADS = TmThreads<C>::value;
   constexpr int CS = C + 4;
-  constexpr int TPB = TM_THREADS / LPT;               // tokens per CTA
+  const int TPB = blockDim.x / LPT;                   // tokens per CTA (blockDim.x <= TmThreads<C>, a multiple of 32)
   extern __shared__ __align__(16) float tm_s[];
   float* sA = tm_s;                                   // fc^T [hid][CS]  /  W1 chunk [jh][CS]  /  wq [hid][CS]
   float* sB = tm_s + (size_t)(p.hid > p.jh ? p.hid : p.jh) * CS;   // W2^T chunk [jh][CS]
@@ -166,9 +165,20 @@ __global__ void __launch_bounds__(TmThreads<C>::value, 1) token_mlp_kernel(const
 }
 
 template <int C, int LPT>
-static int launch_token_mlp2(TokenMlpP& p, cudaStream_t st) {
-  constexpr int TM_THREADS = TmThreads<C>::value;
+static int launch_token_mlp2(TokenMlpP& p, cudaStream_t st, int sms) {
   constexpr int CS = C + 4;
+  // one wave, every SM busy: when the tokens do not fill `sms` full-size CTAs, shrink the CTAs so that each SM
+  // gets ceil(T / sms) tokens instead of leaving SMs idle (level 1: 86 CTAs of 512 -> 138 CTAs of 320 threads)
+  // Every CTA stages ALL the weights whatever its token count, so smaller CTAs only pay off when they bring many
+  // more SMs in: measured 165 -> 126 us at 86 -> 138 CTAs, but 74 -> 111 us at 126 -> 144 CTAs (level 2).
+  int threads = TmThreads<C>::value;
+  const int full = cdiv((long long)p.T * LPT, threads);
+  if (full * 4 < sms * 3) {
+    const int per_sm = cdiv(p.T, sms) * LPT;
+    threads = ((per_sm + 31) / 32) * 32;
+    if (threads > TmThreads<C>::value) threads = TmThreads<C>::value;
+  }
+  const int TM_THREADS = threads;
   int jh = 16384 / C;                                  // ~2 * jh * C * 4 B = 128 KB of weights per chunk
   if (jh > p.dffn) jh = p.dffn;
   p.jh = jh;
@@ -188,12 +198,12 @@ static int launch_token_mlp(TokenMlpP& p, cudaStream_t st) {
   int lpt = 1;
   while (lpt < 32 && cdiv((long long)p.T * (lpt * 2), TmThreads<C>::value) <= sms) lpt <<= 1;
   switch (lpt) {
-    case 1: return launch_token_mlp2<C, 1>(p, st);
-    case 2: return launch_token_mlp2<C, 2>(p, st);
-    case 4: return launch_token_mlp2<C, 4>(p, st);
-    case 8: return launch_token_mlp2<C, 8>(p, st);
-    case 16: return launch_token_mlp2<C, 16>(p, st);
-    default: return launch_token_mlp2<C, 32>(p, st);
+    case 1: return launch_token_mlp2<C, 1>(p, st, sms);
+    case 2: return launch_token_mlp2<C, 2>(p, st, sms);
+    case 4: return launch_token_mlp2<C, 4>(p, st, sms);
+    case 8: return launch_token_mlp2<C, 8>(p, st, sms);
+    case 16: return launch_token_mlp2<C, 16>(p, st, sms);
+    default: return launch_token_mlp2<C, 32>(p, st, sms);
   }
 }
 
