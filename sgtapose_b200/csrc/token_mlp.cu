@@ -59,11 +59,23 @@ __device__ __forceinline__ void allreduce_vec(float (&v)[C]) {
 template <int C>
 __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int n, int tid) {
   constexpr int V = C / 4;
-  const int nthreads = blockDim.x;
+  const int nthreads = blockDim.x;                    // run-time (CTAs may be shrunk): keep four loads in flight by hand
   const float4* s4 = reinterpret_cast<const float4*>(src);
-  for (int i = tid; i < n * V; i += nthreads) {
-    const int r = i / V, v = i - r * V;
-    *reinterpret_cast<float4*>(dst + (size_t)r * (C + 4) + 4 * v) = __ldg(s4 + i);
+  for (int i0 = tid; i0 < n * V; i0 += 4 * nthreads) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < n * V) v[u] = __ldg(s4 + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < n * V) {
+        const int r = i / V, c = i - r * V;
+        *reinterpret_cast<float4*>(dst + (size_t)r * (C + 4) + 4 * c) = v[u];
+      }
+    }
   }
 }
 
