@@ -35,8 +35,10 @@ using namespace umma;
 
 constexpr int TM = 128;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int G_PROD_WARPS = 8;
-constexpr int G_THREADS = (G_PROD_WARPS + 2 + 4) * 32;   // producers, B loader, MMA, 4 epilogue warps
+// producer warps of the gather kernel: the DCN producers are bound by dependent-instruction latency, not by issue
+// slots or loads (tools/dcn_bench.py), so they get 16 warps (2 rows per lane) where the plain gathers keep 8 (4 rows)
+template <int PROD> struct GProd { static constexpr int warps = PROD == 0 ? 16 : 8; };
+template <int PROD> struct GThreads { static constexpr int value = (GProd<PROD>::warps + 2 + 4) * 32; };   // + B loader, MMA, 4 epilogue warps
 constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
                                                          // each, tests/cuda/tma_bw_probe.cu): spread them over 4
 constexpr int S_EPI_NH = 1;                              // epilogue warps per TMEM lane quadrant
@@ -554,7 +556,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
 
 // =============================================================================== gather kernel
 template <int PROD, int NS>
-__global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_constant__ ConvP p) {
+__global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(const __grid_constant__ ConvP p) {
+  constexpr int G_PROD_WARPS = GProd<PROD>::warps;
+  constexpr int RPL = TM / (G_PROD_WARPS * 4);          // rows per lane and K block: 4 (8 warps) or 2 (16 warps)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align1024(smem_raw);
   const int NT = p.NT;
@@ -604,17 +608,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
       if (++pst == p.SA) { pst = 0; pph ^= 1u; }
     };
     const size_t plane_bytes = ((size_t)p.x.nchunks * p.x.rows) << 7;     // PL inputs
-    uint32_t soff[4];      // swizzled byte offset of this thread's 16-byte group in each of its rows
-    int rr[4];
+    uint32_t soff[RPL];    // swizzled byte offset of this thread's 16-byte group in each of its rows
+    int rr[RPL];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      rr[i] = warp * 16 + i * 4 + sub;
+    for (int i = 0; i < RPL; ++i) {
+      rr[i] = warp * (4 * RPL) + i * 4 + sub;
       soff[i] = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
     }
 
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int m0 = (t / p.n_tiles) * TM;
-      if (PROD == PROD_DCN) {
+      if constexpr (PROD == PROD_DCN) {
         // ---- per tile: sampling table in shared memory, one entry per (tap, row): the byte offsets
         // of the four corner rows inside a chunk (16-byte group 0, swizzle folded in: a lane only
         // XORs its own group index) and the four mask*bilinear weights; every lane of a row reads
@@ -659,13 +663,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t sA_s = smem_u32(wait_stage());
             if (p.dbg & 1) { publish(); continue; }
+            constexpr int GRW = RPL == 4 ? 2 : 1;       // rows blended together (loads in flight: GRW x 4 corners x NS)
 #pragma unroll
-            for (int ih = 0; ih < 2; ++ih) {
-              uint4 v[2][4][NS];
-              float4 w[2];
+            for (int ih = 0; ih < RPL / GRW; ++ih) {
+              uint4 v[GRW][4][NS];
+              float4 w[GRW];
 #pragma unroll
-              for (int ii = 0; ii < 2; ++ii) {
-                const int i = ih * 2 + ii;
+              for (int ii = 0; ii < GRW; ++ii) {
+                const int i = ih * GRW + ii;
                 const uint4 o4 = lds128(tab_s + (uint32_t)(tap * TM + rr[i]) * 16u);
                 const uint4 w4 = lds128(tab_s + (uint32_t)(9 * TM + tap * TM + rr[i]) * 16u);
                 w[ii] = make_float4(__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w));
@@ -677,8 +682,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
                 }
               }
 #pragma unroll
-              for (int ii = 0; ii < 2; ++ii) {
-                const int i = ih * 2 + ii;
+              for (int ii = 0; ii < GRW; ++ii) {
+                const int i = ih * GRW + ii;
                 const float wc[4] = {w[ii].x, w[ii].y, w[ii].z, w[ii].w};
                 uint4 e0, e1 = make_uint4(0, 0, 0, 0);
                 if (NS == 2) {
@@ -740,7 +745,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const __grid_
         }
       }
     }
-    if (PROD != PROD_DCN) {
+    if constexpr (PROD != PROD_DCN) {
       // ---- plain gathers (STRIDE: PL input, SMALLC: SC input).  The K blocks of all tiles of this
       // CTA form one flat stream; loads run PD blocks ahead of the shared-memory stores so PD
       // blocks of global-load latency overlap per warp (8 warps per SM cannot hide it otherwise).
@@ -1020,7 +1025,7 @@ static int launch_gather(ConvP& p, cudaStream_t st) {
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
   cudaFuncSetAttribute(conv_gather_kernel<PROD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  conv_gather_kernel<PROD, NS><<<grid, G_THREADS, smem, st>>>(p);
+  conv_gather_kernel<PROD, NS><<<grid, GThreads<PROD>::value, smem, st>>>(p);
   return check_launch("conv_gather_kernel");
 }
 
