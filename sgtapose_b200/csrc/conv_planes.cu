@@ -36,7 +36,8 @@ using namespace umma;
 constexpr int TM = 128;
 constexpr int SMEM_LIMIT = 227 * 1024;
 // producer warps of the gather kernel: the DCN producers are bound by dependent-instruction latency, not by issue
-// slots or loads (tools/dcn_bench.py), so they get 16 warps (2 rows per lane) where the plain gathers keep 8 (4 rows)
+// slots or loads (tools/dcn_bench.py), so they get 16 warps (2 rows per lane) where the plain gathers keep 8 (4 rows;
+// measured with 16: stem unchanged, level0 -5 %, level1 / stride-2 convs +6..+24 %: a net loss)
 template <int PROD> struct GProd { static constexpr int warps = PROD == 0 ? 16 : 8; };
 template <int PROD> struct GThreads { static constexpr int value = (GProd<PROD>::warps + 2 + 4) * 32; };   // + B loader, MMA, 4 epilogue warps
 constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
@@ -750,18 +751,20 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
       // CTA form one flat stream; loads run PD blocks ahead of the shared-memory stores so PD
       // blocks of global-load latency overlap per warp (8 warps per SM cannot hide it otherwise).
       constexpr int PD = 3;
-      uint4 v[PD][4][NS];
+      uint4 v[PD][RPL][NS];
       const int C2 = p.x.nchunks * 2;                   // SC: bytes per input row
       const size_t sc_plane = (size_t)p.x.rows * C2;
       const int seg = c8 / p.seg_groups, within = c8 - seg * p.seg_groups;
       const int my_tiles = blockIdx.x < total ? (total - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       const long long nblk = (long long)my_tiles * nkb;
       int lt = blockIdx.x, lkb = 0;                     // load cursor: tile, K block inside the tile
-      int anchor[4] = {0, 0, 0, 0};
+      int anchor[RPL];
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) anchor[i] = 0;
       auto set_tile = [&](int t) {
         const int m0 = (t / p.n_tiles) * TM;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RPL; ++i) {
           int px, py, b;
           decode_row(p, m0 + rr[i], px, py, b);
           b = min(b, p.x.B - 1);                          // border / tail rows: any in-bounds address
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
           anchor[i] = p.x.guard + b * iHp * iWp + oy * p.stride * iWp + ox * p.stride;
         }
       };
-      auto load_block = [&](uint4 (&dst)[4][NS]) {
+      auto load_block = [&](uint4 (&dst)[RPL][NS]) {
         if (lkb == 0) set_tile(lt);
         if (PROD == PROD_STRIDE) {
           // 3x3, pad 1, stride s: padded input coords of tap (ky,kx) = (oy*s+ky, ox*s+kx); kc outer
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
           const int toff = (tap / 3) * iWp + tap % 3;
           const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < RPL; ++i) {
             const int r = anchor[i] + toff;
             const unsigned char* src = xk + ((size_t)r << 7) + (((c8 ^ r) & 7) << 4);
 #pragma unroll
@@ -789,7 +792,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
             // so the 8 lanes of a row read two contiguous 64-byte runs (the weight matrix uses the same order)
             const int so0 = p.seg_off[lkb * 2], so1 = p.seg_off[lkb * 2 + 1];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPL; ++i) {
               const unsigned char* s0 = p.x.base + (size_t)(anchor[i] + so0) * C2 + c8 * 8;
               const unsigned char* s1 = p.x.base + (size_t)(anchor[i] + so1) * C2 + c8 * 8;
 #pragma unroll
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
             // group c8 of K block kb = 16 bytes at (anchor + seg_off[kb][seg]) * C*2 + within*16
             const int so = p.seg_off[lkb * 2 + seg];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPL; ++i) {
               const unsigned char* src0 = p.x.base + (size_t)(anchor[i] + so) * C2 + within * 16;
 #pragma unroll
               for (int pl = 0; pl < NS; ++pl) dst[i][pl] = __ldg(reinterpret_cast<const uint4*>(src0 + pl * sc_plane));
@@ -812,10 +815,10 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
         }
         if (++lkb == nkb) { lkb = 0; lt += gridDim.x; }
       };
-      auto store_block = [&](const uint4 (&src)[4][NS]) {
+      auto store_block = [&](const uint4 (&src)[RPL][NS]) {
         unsigned char* sA = wait_stage();
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < RPL; ++i)
 #pragma unroll
           for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + soff[i]) = src[i][pl];
         publish();
