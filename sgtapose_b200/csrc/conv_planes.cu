@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t sA_s = smem_u32(wait_stage());
             if (p.dbg & 1) { publish(); continue; }
-            constexpr int GRW = RPL == 4 ? 2 : 1;       // rows blended together (loads in flight: GRW x 4 corners x NS)
+            constexpr int GRW = 2;                      // rows blended together (loads in flight: GRW x 4 corners x NS)
 #pragma unroll
             for (int ih = 0; ih < RPL / GRW; ++ih) {
               uint4 v[GRW][4][NS];
