@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_planes.py tests/test_gpu_ops.py -x -q -k "dcn or engine_golden" > gpurun_out/t_dcn.log 2>&1; echo "dcn tests rc=$?"; tail -2 gpurun_out/t_dcn.log
-timeout 600 python bench.py --no-cpu-baseline --no-extras > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"; python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/bench_quick.json') if l.startswith('{')][-1])
-print(d['value'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['ms_per_step'])
-PY
-tail -3 gpurun_out/bench_quick.err
+timeout 300 python -m pytest tests/test_gpu_planes.py -x -q -k "upsample" > gpurun_out/t_ups.log 2>&1; echo "ups tests rc=$?"; tail -2 gpurun_out/t_ups.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -k regex:upsample -c 8 --csv --log-file gpurun_out/ups_launches.csv python bench.py --profile-pass --no-cpu-baseline > gpurun_out/launches.log 2>&1; grep "upsample" gpurun_out/ups_launches.csv | awk -F'","' '{print $NF}' | tr '\n' ' '
