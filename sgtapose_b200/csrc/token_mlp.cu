@@ -128,20 +128,25 @@ __global__ void __launch_bounds__(TmThreads<C>::value, 1) token_mlp_kernel(const
 #pragma unroll 2
     for (int j = sub; j < nj; j += LPT) {
       const float4* w1r = reinterpret_cast<const float4*>(sA + (size_t)j * CS);
-      float h0 = __ldg(p.b1 + j0 + j), h1 = 0.f;               // two partial sums: shorter FMA chains
+      // channel pairs as packed FFMA2 (sm_100): (h0, h1) += (w.x, w.y) * (x[4c], x[4c+1]) then (w.z, w.w) * (x[4c+2],
+      // x[4c+3]) -- the same two partial sums in the same order as the scalar form; acc pairs += (w.x, w.y) * h with the
+      // scalar h broadcast by the instruction.  Each half is an IEEE fma: results are bit-identical, issue slots halve.
+      float2 hh = make_float2(__ldg(p.b1 + j0 + j), 0.f);
 #pragma unroll
       for (int c4 = 0; c4 < C / 4; ++c4) {
         const float4 w = w1r[c4];
-        h0 = fmaf(w.x, x[4 * c4], h0); h1 = fmaf(w.y, x[4 * c4 + 1], h1);
-        h0 = fmaf(w.z, x[4 * c4 + 2], h0); h1 = fmaf(w.w, x[4 * c4 + 3], h1);
+        hh = __ffma2_rn(make_float2(w.x, w.y), make_float2(x[4 * c4], x[4 * c4 + 1]), hh);
+        hh = __ffma2_rn(make_float2(w.z, w.w), make_float2(x[4 * c4 + 2], x[4 * c4 + 3]), hh);
       }
-      const float h = fmaxf(h0 + h1, 0.f);
+      const float h = fmaxf(hh.x + hh.y, 0.f);
+      const float2 h2 = make_float2(h, h);
       const float4* w2r = reinterpret_cast<const float4*>(sB + (size_t)j * CS);
 #pragma unroll
       for (int c4 = 0; c4 < C / 4; ++c4) {
         const float4 w = w2r[c4];
-        acc[4 * c4] = fmaf(w.x, h, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(w.y, h, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(w.z, h, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(w.w, h, acc[4 * c4 + 3]);
+        const float2 a0 = __ffma2_rn(make_float2(w.x, w.y), h2, make_float2(acc[4 * c4], acc[4 * c4 + 1]));
+        const float2 a1 = __ffma2_rn(make_float2(w.z, w.w), h2, make_float2(acc[4 * c4 + 2], acc[4 * c4 + 3]));
+        acc[4 * c4] = a0.x; acc[4 * c4 + 1] = a0.y; acc[4 * c4 + 2] = a1.x; acc[4 * c4 + 3] = a1.y;
       }
     }
   }
