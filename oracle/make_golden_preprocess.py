@@ -66,11 +66,20 @@ def load_reference_methods():
     return ns["RefPre"], torch
 
 
-def reference_pre_process(image, input_hw):
+MODE_CASES = [  # raw (h, w), opt overrides, seed: the two other testing modes of _transform_scale (meta only is pinned
+    ((360, 640), {"fix_short": 384}, 6),        # on the device side: the warp kernel is mode-independent)
+    ((640, 360), {"fix_short": 320}, 7),
+    ((357, 501), {"fix_res": False}, 8),
+]
+
+
+def reference_pre_process(image, input_hw, **over):
     RefPre, torch = load_reference_methods()
     obj = RefPre()
     obj.opt = types.SimpleNamespace(fix_short=-1, fix_res=True, input_h=input_hw[0], input_w=input_hw[1],
                                     down_ratio=4, pad=31)
+    for k, v in over.items():
+        setattr(obj.opt, k, v)
     obj.mean = torch.tensor([0.5, 0.5, 0.5], dtype=torch.float32).reshape(1, 1, 3)     # sgta_detector.py:58-59
     obj.std = torch.tensor([0.5, 0.5, 0.5], dtype=torch.float32).reshape(1, 1, 3)
     obj.rest_focal_length = 502.30
@@ -89,6 +98,14 @@ def main():
         out["c_%d" % i] = np.asarray(meta["c"], np.float32)
         out["s_%d" % i] = np.float64(meta["s"])
         print(i, raw, inp, images.shape, float(images.min()), float(images.max()))
+    for j, (raw, over, seed) in enumerate(MODE_CASES):
+        img = case_image(raw, seed)
+        images, meta = reference_pre_process(img, (384, 384), **over)
+        out["mode_images_%d" % j] = images[:, :, ::4, ::4].copy()      # every 4th pixel: keeps the fixture small
+        out["mode_trans_input_%d" % j] = np.asarray(meta["trans_input"], np.float64)
+        out["mode_trans_output_%d" % j] = np.asarray(meta["trans_output"], np.float64)
+        out["mode_sizes_%d" % j] = np.array([meta["inp_height"], meta["inp_width"], meta["out_height"], meta["out_width"]])
+        print("mode", j, raw, over, images.shape)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -1,8 +1,8 @@
 """Image pre-processing on the device for a lock-step batch of clips.
 
 Mirrors `SGTADetector._transform_scale` / `pre_process` / `normalize_img`
-(sgtapose/lib/sgta_detector.py:334-366, :368-399, :402-403) for the `fix_res` testing mode the
-reference runs in (opts_parallel.py:341): same `meta` keys, same matrices (the 3-point solve stays
+(sgtapose/lib/sgta_detector.py:334-366, :368-399, :402-403) for test scale 1 in all three testing modes
+(`fix_res`, the one the reference runs in, opts_parallel.py:341; `fix_short`; keep-resolution): same `meta` keys, same matrices (the 3-point solve stays
 `cv2.getAffineTransform` on the host through `get_affine_transform`, lib/utils/image.py:45-78), and
 the network input computed by ONE launch of `sgta_preprocess` from the raw uint8 frames -- cv2's
 fixed-point bilinear warp restated bit-exactly, then ((img / 255.) - mean) / std in float32.
@@ -26,13 +26,31 @@ STD = (0.5, 0.5, 0.5)       # sgta_detector.py:59
 get_affine_transform = PR.get_affine_transform
 
 
-def transform_meta(height, width, opt):
-    """_transform_scale (fix_res branch, scale 1) + the meta dict of pre_process for one raw frame size."""
-    if getattr(opt, "fix_short", -1) > 0 or not getattr(opt, "fix_res", True):
-        raise _lib.SgtaError("pre_process: only the fix_res testing mode of the reference is built")
-    inp_h, inp_w = int(opt.input_h), int(opt.input_w)
-    c = np.array([width / 2., height / 2.], dtype=np.float32)
-    s = max(height, width) * 1.0
+def transform_meta(height, width, opt, scale=1):
+    """_transform_scale (sgta_detector.py:334-366, all three testing modes) + the meta dict of pre_process
+    (:375-394) for one raw frame size.  `fix_res` (the mode the reference runs in, opts_parallel.py:341) is the
+    default; `fix_short` and keep-resolution (`fix_res` False, padded to `opt.pad`) follow the same lines."""
+    new_height, new_width = int(height * scale), int(width * scale)
+    if (new_height, new_width) != (height, width):
+        # cv2.resize before the warp (:365) is a second interpolation the device kernel does not restate
+        raise _lib.SgtaError("pre_process: only test scale 1 is built (the reference's default test_scales)")
+    fix_short = int(getattr(opt, "fix_short", -1))
+    if fix_short > 0:
+        if height < width:
+            inp_h, inp_w = fix_short, (int(width / height * fix_short) + 63) // 64 * 64
+        else:
+            inp_h, inp_w = (int(height / width * fix_short) + 63) // 64 * 64, fix_short
+        c = np.array([width / 2, height / 2], dtype=np.float32)
+        s = np.array([width, height], dtype=np.float32)
+    elif getattr(opt, "fix_res", True):
+        inp_h, inp_w = int(opt.input_h), int(opt.input_w)
+        c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
+        s = max(height, width) * 1.0
+    else:
+        pad = int(getattr(opt, "pad", 31))
+        inp_h, inp_w = (new_height | pad) + 1, (new_width | pad) + 1
+        c = np.array([new_width // 2, new_height // 2], dtype=np.float32)
+        s = np.array([inp_w, inp_h], dtype=np.float32)
     down = int(getattr(opt, "down_ratio", 4))
     out_h, out_w = inp_h // down, inp_w // down
     return {"c": c, "s": s, "height": height, "width": width, "out_height": out_h, "out_width": out_w,

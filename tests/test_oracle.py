@@ -239,3 +239,27 @@ def test_preprocess_host_meta_matches_reference_golden(golden):
         assert (meta["out_height"], meta["out_width"]) == (inp[0] // 4, inp[1] // 4)
     with pytest.raises(Exception):
         pre.warp_normalize(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), np.eye(2, 3), (8, 8))   # no CPU fallback
+
+
+def test_preprocess_other_testing_modes_match_reference_golden(golden):
+    """`fix_short` and keep-resolution modes of _transform_scale (sgta_detector.py:344-362): host meta of the product
+    and the oracle's images (every 4th pixel stored) vs the reference's own pre_process."""
+    import types
+    from oracle import preprocess as opre
+    from oracle.make_golden_preprocess import MODE_CASES, case_image
+    from sgtapose_b200 import preprocess as pre
+    g = golden("preprocess.npz")
+    for j, (raw, over, seed) in enumerate(MODE_CASES):
+        opt = types.SimpleNamespace(fix_res=True, fix_short=-1, input_h=384, input_w=384, down_ratio=4, pad=31)
+        for k, v in over.items():
+            setattr(opt, k, v)
+        meta = pre.transform_meta(raw[0], raw[1], opt)
+        assert np.array_equal(meta["trans_input"], g["mode_trans_input_%d" % j]), j
+        assert np.array_equal(meta["trans_output"], g["mode_trans_output_%d" % j]), j
+        sizes = [meta["inp_height"], meta["inp_width"], meta["out_height"], meta["out_width"]]
+        assert sizes == g["mode_sizes_%d" % j].tolist(), j
+        warped = opre.warp_affine_u8(case_image(raw, seed), meta["trans_input"], (meta["inp_width"], meta["inp_height"]))
+        x = opre.normalize(warped, np.full((1, 1, 3), 0.5, np.float32), np.full((1, 1, 3), 0.5, np.float32))
+        assert np.array_equal(x.transpose(2, 0, 1)[None][:, :, ::4, ::4], g["mode_images_%d" % j]), j
+    with pytest.raises(Exception):
+        pre.transform_meta(360, 640, types.SimpleNamespace(fix_res=True, input_h=384, input_w=384), scale=0.5)

@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -k regex:token_mlp -c 9 --csv --log-file gpurun_out/tok_launches.csv python bench.py --profile-pass --no-cpu-baseline > gpurun_out/launches.log 2>&1; grep "token_mlp" gpurun_out/tok_launches.csv | awk -F'","' '{print substr($5,6,28), $NF}' | tr -d '"' | tr '\n' '|'
+timeout 500 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/t_all.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
