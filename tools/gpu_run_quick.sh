@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/t_all.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
+timeout 200 python bench.py --mode bf16 --no-extras --no-cpu-baseline > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench rc=$?"; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/bench_bf16.json') if l.startswith('{')][-1])
+print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['achieved'], d['roofline']['ms_per_step'])
+PY
