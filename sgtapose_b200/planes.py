@@ -108,6 +108,37 @@ def weight_matrix(weight, cin_pad=None, cin_off=0):
     return wm.reshape(Cout, kh * kw * cin_pad)
 
 
+def superpixel_weight(weight, gin, gout, stride=1):
+    """Toeplitz expansion of a 3x3 convolution on `[pixels][C]` rows into a 3x3 convolution over SUPER-PIXELS
+    (g consecutive pixels x C channels, channel index j*C + c): weight [Co,Ci,3,3] -> [gout*Co, gin*Ci, 3, 3],
+    row stride `stride`, super-column stride `stride*gout/gin`, zero border of one super-pixel.
+    With gin*Ci = 64 a small-channel layer (level0: 16 -> 16, level1: 16 -> 32) becomes a plain PL convolution that
+    conv_shift_kernel / conv_gather_kernel<STRIDE> run as they are (host half of that plan, checked
+    against F.conv2d in tests/test_planes_host.py -- the engine does not use it yet)."""
+    Co, Ci, kh, kw = weight.shape
+    if (kh, kw) != (3, 3) or (stride * gout) % gin:
+        raise ValueError("superpixel_weight: 3x3 kernels, stride*gout divisible by gin")
+    out = weight.new_zeros(gout * Co, gin * Ci, 3, 3)
+    for j_out in range(gout):
+        for n in (-1, 0, 1):
+            for j_in in range(gin):
+                dx = gin * n + j_in - stride * j_out          # input pixel offset this (tap, pixel) pair stands for
+                if -1 <= dx <= 1:
+                    out[j_out * Co:(j_out + 1) * Co, j_in * Ci:(j_in + 1) * Ci, :, n + 1] = weight[:, :, :, dx + 1]
+    return out
+
+
+def to_superpixels(x, g):
+    """[B,C,H,W] -> [B,g*C,H,W/g] (channel j*C + c = pixel j of the group): the NCHW view of the super-pixel layout."""
+    B, C, H, W = x.shape
+    return x.reshape(B, C, H, W // g, g).permute(0, 4, 1, 2, 3).reshape(B, g * C, H, W // g)
+
+
+def from_superpixels(x, g):
+    B, GC, H, Ws = x.shape
+    return x.reshape(B, g, GC // g, H, Ws).permute(0, 2, 3, 4, 1).reshape(B, GC // g, H, Ws * g)
+
+
 class ConvSpec:
     """Packed weights + folded scale/shift of one convolution on a PL input."""
 
