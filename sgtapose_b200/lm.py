@@ -48,3 +48,27 @@ def get_weights(num_pt, distance):
     weights[:num_pt] = np.exp(-5 * np.asarray(distance, float)[:num_pt])
     weights[-1:] = 1e8
     return weights.tolist()
+
+
+def get_weights_real(x2d_input, x3d_input, transform, camera):
+    """LM.py:309-332: weights from the squared reprojection distance of every coordinate under `transform` (3x4 or 4x4
+    pose): 0 beyond 100 px^2, 1 below 1 px^2, 1000^(1 - d/10) / 1000 between; points flagged missing (x < -1000) keep
+    weight 0.  -> (weights [num_points+1, 2] ndarray, num_points)."""
+    x2d_input, x3d_input = np.asarray(x2d_input, float), np.asarray(x3d_input, float)
+    num_points = x2d_input.shape[0]
+    weights = np.zeros((num_points + 1, 2))
+    P = np.asarray(camera, float) @ np.asarray(transform, float)[0:3]
+    for i in range(num_points):
+        if x2d_input[i, 0] < -1000:
+            continue
+        rep = P @ np.append(x3d_input[i], 1.0)
+        dis = (rep[:2] / rep[2] - x2d_input[i]) ** 2
+        for j in range(2):
+            if dis[j] > 100:
+                weights[i, j] = 0
+            elif dis[j] < 1:
+                weights[i, j] = 1
+            else:
+                weights[i, j] = np.power(1000, (1 - (dis[j] / 10))) / 1000
+    weights[-1] = [1e8, 1e8]
+    return weights, num_points

@@ -106,3 +106,29 @@ def test_oracle_residuals_and_jacobian_match_reference_twin():
         J_ref = np.array(ns["dfun"](v, x2d.tolist(), x3d.tolist(), w.tolist(), K), float)
         np.testing.assert_allclose(olm.fun(v, x2d, x3d, w, K), F_ref, rtol=1e-10, atol=1e-9)
         np.testing.assert_allclose(olm.dfun(v, x2d, x3d, w, K), J_ref, rtol=1e-9, atol=1e-6)
+
+
+@pytest.mark.reference
+def test_get_weights_real_matches_reference():
+    from sgtapose_b200 import lm
+    path = os.path.join(ref_import.REF_PKG, "rf_tools", "LM.py")
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("get_weights_real", "get_weights")]
+    mod = ast.Module(body=keep, type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"np": np}
+    exec(compile(mod, path, "exec"), ns)
+    rng = np.random.default_rng(9)
+    K = np.array([[502.30, 0.0, 319.75], [0.0, 502.30, 179.75], [0.0, 0.0, 1.0]])
+    T = np.eye(4)
+    T[:3, :3] = olm.rotation_from_quaternion(rng.normal(size=4))
+    T[:3, 3] = [0.1, -0.05, 1.5]
+    X = rng.uniform(-0.3, 0.3, (7, 3))
+    uv = (K @ (T[:3] @ np.c_[X, np.ones(7)].T)).T
+    uv = uv[:, :2] / uv[:, 2:] + rng.choice([0.3, 2.0, 15.0], size=(7, 2)) * rng.choice([-1, 1], size=(7, 2))
+    uv[3] = [-5000.0, -5000.0]                                   # flagged missing
+    w_ref, n_ref = ns["get_weights_real"](uv, X, T, K)
+    w, n = lm.get_weights_real(uv, X, T, K)
+    assert n == n_ref == 7 and np.array_equal(w, w_ref)
+    d = rng.uniform(0, 1, (7, 2))
+    assert np.allclose(np.array(lm.get_weights(7, d)), np.array(ns["get_weights"](7, d)), rtol=1e-15, atol=0)
