@@ -263,3 +263,61 @@ def test_preprocess_other_testing_modes_match_reference_golden(golden):
         assert np.array_equal(x.transpose(2, 0, 1)[None][:, :, ::4, ::4], g["mode_images_%d" % j]), j
     with pytest.raises(Exception):
         pre.transform_meta(360, 640, types.SimpleNamespace(fix_res=True, input_h=384, input_w=384), scale=0.5)
+
+
+# ------------------------------------------------------------------------------------ decode rounding bound
+def test_decode_float32_blur_stays_inside_the_band_the_kernel_uses():
+    """The production decode kernel blurs in float32 and trusts a comparison only when its margin exceeds
+    80 * 2^-24 * (v32 for non-negative maps | max|x| otherwise) per value (csrc/decode.cu).  Emulate that blur in numpy
+    float32 (25 sequential multiply-adds per pass; numpy does not fuse them, which can only be less accurate than the
+    kernel's FMA chain) and check on representative maps that the distance to the oracle's float64-accumulate /
+    float32-store result is inside the band with margin, and that the banded classification never contradicts the
+    reference predicate (no false "surely a peak", no false "surely not")."""
+    w64 = odec.gaussian_weights()
+    wf = w64.astype(np.float32)
+    U = np.float32(80.0 * 2.0 ** -24)
+
+    def blur32(m):
+        h, w = m.shape
+        iy = np.array([[odec._reflect(y - 12 + t, h) for t in range(25)] for y in range(h)])
+        ix = np.array([[odec._reflect(x - 12 + t, w) for t in range(25)] for x in range(w)])
+        tmp = (m[iy[:, 0], :] * wf[0]).astype(np.float32)
+        for t in range(1, 25):
+            tmp = (tmp + m[iy[:, t], :] * wf[t]).astype(np.float32)
+        out = (tmp[:, ix[:, 0]] * wf[0]).astype(np.float32)
+        for t in range(1, 25):
+            out = (out + tmp[:, ix[:, t]] * wf[t]).astype(np.float32)
+        return out
+
+    rng = np.random.default_rng(0)
+    hm, _ = synth.synthetic_heatmaps(2, 7, 96, 96, seed=3, noise=0.02, missing_every=4)
+    maps = [hm.numpy()[b, c] for b in range(2) for c in range(7)]
+    maps += [rng.random((96, 96), dtype=np.float32), (0.01 + 0.002 * rng.standard_normal((96, 96))).astype(np.float32),
+             np.full((96, 96), 0.5, np.float32), rng.standard_normal((40, 17)).astype(np.float32),
+             (1e-3 * rng.random((120, 120))).astype(np.float32)]
+    worst = 0.0
+    for m in maps:
+        v, ref = blur32(m), odec.gaussian_blur(m)
+        nonneg = m.min() >= 0
+        ev = (U * v).astype(np.float32) if nonneg else np.full_like(v, U * np.float32(np.abs(m).max()))
+        err = np.abs(v.astype(np.float64) - ref.astype(np.float64))
+        assert (err <= 0.5 * ev.astype(np.float64) + 1e-45).all()             # at least 2x inside the band
+        worst = max(worst, float((err / np.maximum(ev.astype(np.float64), 1e-300)).max()))
+        h, w = m.shape
+        pad = np.zeros((h + 2, w + 2), np.float32); pad[1:-1, 1:-1] = v
+        pev = np.zeros((h + 2, w + 2), np.float32); pev[1:-1, 1:-1] = ev
+        padr = np.zeros((h + 2, w + 2), np.float32); padr[1:-1, 1:-1] = ref
+        T = np.float32(0.01)
+        no, sure = v < T - ev, v > T + ev
+        peak = ref > T
+        for sl in ((slice(0, -2), slice(1, -1)), (slice(2, None), slice(1, -1)), (slice(1, -1), slice(0, -2)),
+                   (slice(1, -1), slice(2, None))):
+            nb, band = pad[sl], ev + (pev[sl] if nonneg else ev)
+            inside = np.zeros((h + 2, w + 2), bool); inside[1:-1, 1:-1] = True
+            band = np.where(inside[sl], band, ev)                              # neighbours outside the map are exact zeros
+            d = v - nb
+            no |= d < -band
+            sure &= d > band
+            peak &= ref >= padr[sl]
+        assert not (no & peak).any() and not (sure & ~peak).any()
+    assert worst < 0.2                                                         # measured: a few ulps against a bound of 80
