@@ -316,6 +316,11 @@ int sgta_token_mlp(const void* att, const void* q, const void* fc_wt, const void
 int sgta_render_priors(const void* centres_in, const void* centres_out, void* hm, void* hm_cls,
                        const float* gauss9x9, int B, int K, int H, int W, int h, int w, void* stream);
 
+/* Super-pixel view of a 16-channel SC map (round-2 plan; not on the default path yet):
+ * sc = SC view, 16 channels, [B,H,W];  sp = PL view, 64 channels (4 pixels x 16 channels), [B,H,W/4].
+ * to_super != 0: sc -> sp, else sp -> sc.  Raw 16-byte moves; border super-pixels are left untouched (zero). */
+int sgta_planes_superpixels(const sgta_planes* sc, const sgta_planes* sp, int to_super, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Image pre-processing: SGTADetector.pre_process
  * (sgtapose/lib/sgta_detector.py:368-399) = cv2.warpAffine(image, trans_input, (W, H), INTER_LINEAR)

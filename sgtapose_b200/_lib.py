@@ -43,6 +43,7 @@ SIGNATURES = {
     "sgta_planes_pack_stem": (_I, [_P, _P, _V, _I, _I, _P]),
     "sgta_planes_maxpool2": (_I, [_V, _I, _V, _I, _I, _P]),
     "sgta_planes_upsample_add": (_I, [_V, _P, _V, _V, _I, _I, _P]),
+    "sgta_planes_superpixels": (_I, [_V, _V, _I, _P]),
     "sgta_planes_gather_tokens": (_I, [_V, _I, _P, _P, _I, _I, _I, _P]),
     "sgta_planes_scatter_tokens": (_I, [_V, _I, _P, _P, _I, _I, _I, _P]),
     "sgta_abi_version": (_I, []),

@@ -151,6 +151,31 @@ pl_upsample_add_kernel(View x, const float* __restrict__ w, View skip, int has_s
   }
 }
 
+// ---- super-pixel views ----------------------------------------------------------
+// A [rows][16 ch] SC map read as [rows / 4][4 px x 16 ch]: one 128-byte PL row per SUPER-PIXEL (channel index
+// j*16 + c for pixel j of the group), frame (H+2) x (W/4+2) with the usual one-(super-)pixel zero border, so
+// that a small-channel 3x3 convolution becomes a plain PL convolution with Toeplitz-expanded weights
+// (planes.superpixel_weight) that conv_shift_kernel runs as it stands.  Raw 16-byte moves, no arithmetic:
+// group g of a super-pixel row = channels [8*(g&1), +8) of pixel g>>1.
+template <int NS>
+__global__ void pl_sc16_super4_kernel(View sc, View sp, int to_super, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int g = (int)(e & 7);
+  long long r = e >> 3;
+  const int xs = (int)(r % sp.W);
+  r /= sp.W;
+  const int y = (int)(r % sp.H), b = (int)(r / sp.H);
+  const long long p_sc = frame_row(sc, b, y, 4 * xs + (g >> 1)), p_sp = frame_row(sp, b, y, xs);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    unsigned char* a = sc.base + sc_offset(sc, s, p_sc, (g & 1) * 8);
+    unsigned char* d = sp.base + pl_offset(sp, s, 0, p_sp, g);
+    if (to_super) *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(a));
+    else *reinterpret_cast<uint4*>(a) = __ldg(reinterpret_cast<const uint4*>(d));
+  }
+}
+
 // ---- tokens -----------------------------------------------------------------------------------
 // rows[b,t,:] = feats[b, :, ids[b,t]]  (ids = y*W + x in the unpadded map); images
 // [b_off, b_off+B) of the view
@@ -254,6 +279,17 @@ extern "C" int sgta_planes_maxpool2(const sgta_planes* x, int xc_off, const sgta
   View vx = make_view(x), vy = make_view(y);
   NS_DISPATCH(x->nplanes, (pl_maxpool2_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, C, xc_off, yc_off, total)));
   return check_launch("pl_maxpool2_kernel");
+}
+
+extern "C" int sgta_planes_superpixels(const sgta_planes* sc, const sgta_planes* sp, int to_super, void* stream) {
+  SGTA_REQUIRE(geom_ok(sc) && geom_ok(sp) && sc->layout == SGTA_LAYOUT_SC && sc->nchunks == 16 && sc->border == 1 &&
+               sp->layout == SGTA_LAYOUT_PL && sp->border == 1 && chan_ok(sp, 0, 64) && sc->nplanes == sp->nplanes &&
+               sc->B == sp->B && sc->H == sp->H && sc->W == 4 * sp->W,
+               "sgta_planes_superpixels: sc = SC view with 16 channels, sp = PL view with 64 channels and W / 4 columns");
+  const long long total = (long long)sp->B * sp->H * sp->W * 8;
+  View vsc = make_view(sc), vsp = make_view(sp);
+  NS_DISPATCH(sc->nplanes, (pl_sc16_super4_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(vsc, vsp, to_super, total)));
+  return check_launch("pl_sc16_super4_kernel");
 }
 
 extern "C" int sgta_planes_upsample_add(const sgta_planes* x, const void* w_up, const sgta_planes* skip,

@@ -43,7 +43,7 @@ def _fold_bn(sd, p, bias=None):
 
 class InferenceEngine:
     def __init__(self, state_dict, opt, batch, size=384, mode="fp32", device="cuda", fuse_sigmoid=False,
-                 skip_dead_levels=False, use_graph=True):
+                 skip_dead_levels=False, use_graph=True, superpixel_level0=False):
         if mode not in ("fp32", "bf16"):
             raise ValueError("mode must be 'fp32' or 'bf16'")
         if size % 32:
@@ -54,6 +54,10 @@ class InferenceEngine:
         self.opt = opt
         self.fuse_sigmoid = fuse_sigmoid
         self.skip_dead_levels = skip_dead_levels
+        # EXPERIMENTAL, off by default, not yet validated on a GPU: run base.level0 as a 64 -> 64 PL
+        # convolution over super-pixels (4 px x 16 ch) on conv_shift_kernel, with a layout copy on either side.
+        # tools/superpixel_level0_check.py compares it with the default path.
+        self.superpixel_level0 = bool(superpixel_level0)
         self.K_list = [int(getattr(opt, "k_list_%d" % (i + 1))) for i in range(6)]
         self.kernel_list = [int(getattr(opt, "ks%d" % (i + 1))) for i in range(6)]
         self.use_pos = bool(getattr(opt, "pos_embed", True))
@@ -101,6 +105,11 @@ class InferenceEngine:
         s["stem"] = P.ScConvSpec([(wi, 0), (wh, 3)], torch.cat([sa, sb]), torch.cat([ta, tb]), 4, 7, 1, 3, 3, S,
                                  self.ns)
         s["level0"] = self._sc_conv_bn("base.level0.0", "base.level0.1", 1, S, P.ACT_RELU)
+        if self.superpixel_level0:
+            w0 = sd["base.level0.0.weight"].float()
+            sc0, sh0 = _fold_bn(sd, "base.level0.1")
+            s["level0_sp"] = P.ConvSpec(P.weight_matrix(P.superpixel_weight(w0, 4, 4, 1)), sc0.repeat(4), sh0.repeat(4),
+                                        64, 3, 1, self.ns, P.ACT_RELU)
         s["level1"] = self._sc_conv_bn("base.level1.0", "base.level1.1", 2, S, P.ACT_RELU)
         # level2 = Tree(1, 32 -> 64, stride 2): its entry convolutions read SC maps
         l2 = {"c1": self._sc_conv_bn("base.level2.tree1.conv1", "base.level2.tree1.bn1", 2, S // 2, P.ACT_RELU),
@@ -148,6 +157,9 @@ class InferenceEngine:
         b["in4"] = pb(B2, 4, S, border=3)
         b["f0"] = pb(B2, 16, S)
         b["l0"] = pb(B2, 16, S)
+        if self.superpixel_level0:
+            b["sp_in"] = P.PlaneBuf(B2, 64, S, S // 4, ns, dev)
+            b["sp_out"] = P.PlaneBuf(B2, 64, S, S // 4, ns, dev)
         b["l1"] = pb(B2, 32, h1)
         b["bot2"] = pb(B2, 32, h2)
         b["res2"] = pb(B2, 64, h2)
@@ -271,7 +283,12 @@ class InferenceEngine:
         P.pack_stem(i["pre_img"], i["pre_hm"], b["in4"].full, 0)
         P.pack_stem(i["x"], i["repro_hm"], b["in4"].full, B)
         P.conv_sc(s["stem"], b["in4"].full, b["f0"].full, P.EPI_STEM)
-        P.conv_sc(s["level0"], b["f0"].full, b["l0"].full, P.EPI_SC)
+        if self.superpixel_level0:
+            P.superpixels(b["f0"].full, b["sp_in"].full, True)
+            P.conv(s["level0_sp"], b["sp_in"].full, b["sp_out"].full)
+            P.superpixels(b["l0"].full, b["sp_out"].full, False)
+        else:
+            P.conv_sc(s["level0"], b["f0"].full, b["l0"].full, P.EPI_SC)
         P.conv_sc(s["level1"], b["l0"].full, b["l1"].full, P.EPI_SC)
         # level 2: Tree(1, 32->64, stride 2)
         P.maxpool2(b["l1"].full, b["bot2"].full, 32)

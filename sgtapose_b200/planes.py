@@ -266,6 +266,11 @@ def upsample_add(x, w_up, skip, y, C, f):
               _lib.stream())
 
 
+def superpixels(sc, sp, to_super=True):
+    """SC view (16 channels, [B,H,W]) <-> PL super-pixel view (64 channels, [B,H,W/4]); see superpixel_weight."""
+    _lib.call("sgta_planes_superpixels", sc.ref, sp.ref, int(bool(to_super)), _lib.stream())
+
+
 def gather_tokens(x, b_off, ids, C):
     B, n = ids.shape
     rows = torch.empty(B, n, C, device=ids.device, dtype=torch.float32)
