@@ -63,72 +63,10 @@ int sgta_dcn_backward(const void* x, const void* offset_mask, const void* weight
                       int W, int kh, int kw, int stride, int pad, int dil, int dgroups,
                       int dtype, void* stream);
 
-/* ---------------------------------------------------------------------------------
- * B200 fast path: NHWC implicit-GEMM convolutions on tcgen05 / TMEM (conv_umma.cu).
- *   y[p,o] = act( scale[o] * sum_k A[p,k] W[k,o] + shift[o] (+ res[p,o]) )
- * mode: SGTA_MMA_BF16  = bf16 activations/weights, fp32 accumulate;
- *       SGTA_MMA_F32X3 = fp32 activations, hi/lo bf16 split of both operands, three MMAs per
- *                        K step (~2^-16 relative): the fp32 parity mode.
- * Activation dtype is tied to the mode (bf16 / fp32); outputs may be either.
- * --------------------------------------------------------------------------------- */
-#define SGTA_MMA_BF16 0
-#define SGTA_MMA_F32X3 1
+/* activation applied by the convolution epilogues of the engine path below */
 #define SGTA_ACT_NONE 0
 #define SGTA_ACT_RELU 1
 #define SGTA_ACT_SIGMOID 2
-/* epi (NHWC path): 0 = y[p*ldy + o]; 1 = stem, Cout==32: y[p*ldy + c] = relu(a[c]) +
- * relu(a[16+c]), c<16; 2 = fp32 NCHW y[(b*n_valid + o)*Ho*Wo + pix], o < n_valid */
-
-/* DCNv2 (3x3, stride 1, pad 1, dil 1, dg 1: the configuration dla.py:545 constructs),
- * Cin % 64 == 0, Cout % 16 == 0, 16 <= Cout <= 256.
- *   x            [B,H,W,Cin]  bf16 (BF16) / fp32 (F32X3)
- *   offset_mask  [B,H,W,32]   fp32 raw conv_offset_mask output (channels 0..26 used; the mask
- *                             sigmoid and the bilinear gather are fused into the A producer)
- *   wpack        from sgta_dcn_pack_weight (buffer of sgta_dcn_wpack_bytes bytes)
- *   scale, shift [Cout] fp32  (DCN bias and eval-BatchNorm folded: dla.py:547-550)
- *   y            [B,H,W,Cout] fp32 or bf16 (out_dtype) */
-int64_t sgta_dcn_wpack_bytes(int Cin, int Cout, int mode);
-int sgta_dcn_pack_weight(const void* weight_f32 /*[Cout,Cin,3,3]*/, void* wpack, int Cin,
-                         int Cout, int mode, void* stream);
-int sgta_dcn_forward_nhwc(const void* x, const void* offset_mask, const void* wpack,
-                          const void* scale, const void* shift, void* y, int B, int Cin,
-                          int Cout, int H, int W, int mode, int relu, int out_dtype,
-                          void* stream);
-
-/* Plain convolutions (dla.py:41-69 BasicBlock, :157-175 Root, :212-216 project, :241-270
- * stems, :302-312 conv levels; base_model.py:121-135 heads).  The weight is given as a matrix
- * Wm [Cout][Kpad] fp32 with K = (tap, channel), channel fastest, zero padded to Kpad % 64 == 0;
- * Cout % 16 == 0; Cin % 64 == 0 or Cin a power of two in [4,32].
- * ldx / ldres / ldy: pixel strides in elements (>= channels; lets a conv read or write a
- * channel slice of a wider NHWC buffer, e.g. the Root concat).  res may be NULL. */
-int sgta_conv_ntile(int Cout, int mode);
-int64_t sgta_conv_wpack_bytes(int Cout, int Kpad, int mode);
-int sgta_conv_pack_weight(const void* wm_f32, void* wpack, int Cout, int Kpad, int mode,
-                          void* stream);
-int sgta_conv_forward_nhwc(const void* x, int64_t ldx, const void* wpack, const void* scale,
-                           const void* shift, const void* res, int64_t ldres, void* y,
-                           int64_t ldy, int B, int H, int W, int Cin, int Cout, int kh, int kw,
-                           int stride, int pad, int mode, int act, int out_dtype, int res_dtype,
-                           int epi, int n_valid, void* stream);
-
-/* Memory-bound NHWC helpers (elementwise.cu). dtype: SGTA_DTYPE_F32 / SGTA_DTYPE_BF16. */
-int sgta_nchw_to_nhwc(const void* src_f32, void* dst, int B, int C, int HW, int64_t ld, int coff,
-                      int dst_dtype, void* stream);
-int sgta_nhwc_to_nchw(const void* src, void* dst_f32, int B, int C, int HW, int64_t ld, int coff,
-                      int src_dtype, void* stream);
-/* nn.MaxPool2d(2, 2) of Tree.downsample (dla.py:209-210) */
-int sgta_maxpool2x2_nhwc(const void* x, int64_t ldx, void* y, int64_t ldy, int B, int H, int W,
-                         int C, int dtype, void* stream);
-/* IDAUp: y = ConvTranspose2d(C,C,2f,stride=f,padding=f/2,groups=C)(x) + skip  (dla.py:561-577);
- * x [B,h,w,C] dense, w_up [C,1,2f,2f] fp32, skip/y [B,h*f,w*f,*] with pixel strides */
-int sgta_upsample_add_nhwc(const void* x, const void* w_up, const void* skip, int64_t ldskip,
-                           void* y, int64_t ldy, int B, int h, int w, int C, int f, int dtype,
-                           void* stream);
-/* token gather / write-back on NHWC maps of either dtype (rows are fp32 [B,n,C]) */
-int sgta_gather_tokens_nhwc(const void* feats, int64_t ld, const void* ids, void* rows, int B,
-                            int C, int HW, int n, int dtype, void* stream);
-int sgta_scatter_tokens_nhwc(void* feats, int64_t ld, const void* ids, const void* rows, int B,
-                             int C, int HW, int n, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * B200 engine path: zero-bordered "planes" activation layouts + tcgen05 shift-GEMM /
@@ -343,8 +281,12 @@ int sgta_preprocess(const void* img_u8, void* out, void* out_u8, const double* t
  *   x2d [n,2] detected keypoints (pixels), x3d [n,3] keypoints in the robot frame
  *   weights [2n+2]  per-coordinate weights, last two = the unit-quaternion constraint weights (1e8)
  *   camera [9]      row-major 3x3 intrinsics;   ans [7] refined qw qx qy qz tx ty tz
- * Minimises sum_k F_k^2 with F as in LM.py `fun` (:128-156).  `LM` is the same entry under the
- * reference's own symbol name and argument list (void return; NaN in `ans` on failure). */
+ * Minimises sum_k F_k^2 with F as in LM.py `fun` (:128-156), any num_points >= 1.
+ * `LM` is the drop-in: the reference's own symbol name, argument list and iteration, the final iterate
+ * returned as it is (finite or NaN/Inf, exactly what the reference binary hands back).
+ * `sgta_lm_refine` is the same iteration plus ONE DELIBERATE DEVIATION: a result that puts a weighted
+ * keypoint behind the camera (a mirror pose the chaotic Gauss-Newton can land on) is returned as NaN, so
+ * that the caller's existing NaN fall-back (analysis.py:206-210) keeps the PnP pose. */
 int sgta_lm_refine(const double* value_init, const double* x2d, const double* x3d, const double* weights,
                    const double* camera, double* ans, int num_points);
 void LM(double* value_init, double* x2d, double* x3d, double* weights, double* camera, double* ans, int num_points);

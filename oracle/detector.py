@@ -5,6 +5,9 @@ Only tests/ may import this.  Per-item loops, written like the reference:
   merge_outputs                sgtapose/lib/sgta_detector.py:955-961
   _get_final_kps               sgtapose/lib/sgta_detector.py:608-651 (is_ct branch)
   _get_further_dt_pnp_inputs_real   :501-547 (x3d given instead of read from JSON), rendering via oracle/priors.py
+  is_pnp / solve_pnp           sgtapose/geometric_vision.py:283-310, :43-116 -- the rotation comes from cv2.Rodrigues
+                               here (the reference goes rvec -> pyrr quaternion -> matrix33; pyrr is absent), pinned to
+                               the reference functions' own outputs in tests/golden/pnp.npz (tests/test_oracle.py)
 """
 import numpy as np
 
@@ -42,7 +45,32 @@ def final_kps(dets, num_classes):
     return out
 
 
-def further_inputs(kps_detected, x3d_prev, x3d_next, camera_K, trans_input, trans_output, S, q, raw_w, raw_h, is_pnp):
+def solve_pnp(points, projs, camera_K):
+    import cv2
+    if len(points) == 0:
+        return False, None, None
+    try:
+        obj, img = np.asarray(points, np.float64).reshape(-1, 1, 3), np.asarray(projs, np.float64).reshape(-1, 1, 2)
+        ok, rvec, tvec = cv2.solvePnP(obj, img, camera_K, np.array([]), flags=cv2.SOLVEPNP_EPNP)
+        ok, rvec, tvec = cv2.solvePnP(obj, img, camera_K, np.array([]), flags=cv2.SOLVEPNP_ITERATIVE,
+                                      useExtrinsicGuess=True, rvec=rvec, tvec=tvec)
+        return ok, tvec[:, 0], cv2.Rodrigues(rvec)[0]
+    except Exception:
+        return False, None, None
+
+
+def is_pnp(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K):
+    ok, t, R = solve_pnp(prev_pos, prev_projs, camera_K)
+    if not ok:
+        return prev_projs_all, prev_projs_all
+    est = []
+    for x in next_pos:                                   # one point at a time, like point_projection_from_3d
+        pc = camera_K @ (R @ x + t)
+        est.append([pc[0] / pc[2], pc[1] / pc[2]])
+    return prev_projs_all, np.array(est)
+
+
+def further_inputs(kps_detected, x3d_prev, x3d_next, camera_K, trans_input, trans_output, S, q, raw_w, raw_h):
     """-> (pre_hm [S,S], repro_hm [S,S], pre_hm_cls [K,q,q], repro_hm_cls [K,q,q]) of ONE clip."""
     n_kp = x3d_prev.shape[0]
     good = np.unique(np.where(kps_detected > MISSING)[0])

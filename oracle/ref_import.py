@@ -77,10 +77,12 @@ def _load(dotted, path):
     return mod
 
 
-def load_reference(dcn_cls=None):
+def load_reference(dcn_cls=None, dcn_shim_dir=None):
     """Return a namespace with the reference's dla, base_model, utils, decode,
     image_proc and spatial_softmax modules, ``dla.DCN`` bound to ``dcn_cls``
-    (default: the torchvision stand-in)."""
+    (default: the torchvision stand-in).  With ``dcn_shim_dir`` the reference's own relative import
+    (``dla.py:22``) resolves ``DCNv2/dcn_v2.py`` from that directory instead -- the way a maintainer
+    installs the shim of ``integration/`` (level 1)."""
     if not reference_available():
         raise RuntimeError("reference tree not found at %s" % REF_ROOT)
     dcn_cls = dcn_cls or TorchvisionDCN
@@ -99,10 +101,13 @@ def load_reference(dcn_cls=None):
     pkg("sgtapose.lib.model", os.path.join(REF_PKG, "lib", "model"))
     nets = os.path.join(REF_PKG, "lib", "model", "networks")
     pkg("sgtapose.lib.model.networks", nets)
-    pkg("sgtapose.lib.model.networks.DCNv2", os.path.join(nets, "DCNv2"))
-    dcn_mod = types.ModuleType("sgtapose.lib.model.networks.DCNv2.dcn_v2")
-    dcn_mod.DCN = dcn_cls
-    sys.modules[dcn_mod.__name__] = dcn_mod
+    if dcn_shim_dir is not None:
+        pkg("sgtapose.lib.model.networks.DCNv2", dcn_shim_dir)
+    else:
+        pkg("sgtapose.lib.model.networks.DCNv2", os.path.join(nets, "DCNv2"))
+        dcn_mod = types.ModuleType("sgtapose.lib.model.networks.DCNv2.dcn_v2")
+        dcn_mod.DCN = dcn_cls
+        sys.modules[dcn_mod.__name__] = dcn_mod
     # image_proc.py:7,13 import matplotlib.pyplot and webcolors, unused on this path
     for stub in ("matplotlib", "matplotlib.pyplot", "webcolors"):
         if stub not in sys.modules:

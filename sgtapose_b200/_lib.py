@@ -51,19 +51,6 @@ SIGNATURES = {
     "sgta_launch_count": (_c.c_int64, []),
     "sgta_dcn_forward": (_I, [_P] * 5 + [_I] * 12 + [_P]),
     "sgta_dcn_backward": (_I, [_P] * 8 + [_I] * 12 + [_P]),
-    "sgta_dcn_wpack_bytes": (_c.c_int64, [_I, _I, _I]),
-    "sgta_dcn_pack_weight": (_I, [_P, _P, _I, _I, _I, _P]),
-    "sgta_dcn_forward_nhwc": (_I, [_P] * 6 + [_I] * 8 + [_P]),
-    "sgta_conv_ntile": (_I, [_I, _I]),
-    "sgta_conv_wpack_bytes": (_c.c_int64, [_I, _I, _I]),
-    "sgta_conv_pack_weight": (_I, [_P, _P, _I, _I, _I, _P]),
-    "sgta_conv_forward_nhwc": (_I, [_P, _L, _P, _P, _P, _P, _L, _P, _L] + [_I] * 15 + [_P]),
-    "sgta_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _L, _I, _I, _P]),
-    "sgta_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _L, _I, _I, _P]),
-    "sgta_maxpool2x2_nhwc": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P]),
-    "sgta_upsample_add_nhwc": (_I, [_P, _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
-    "sgta_gather_tokens_nhwc": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "sgta_scatter_tokens_nhwc": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),
     "sgta_attn_forward": (_I, [_P] * 5 + [_I] * 5 + [_F, _P]),
     "sgta_attn_backward": (_I, [_P] * 9 + [_I] * 5 + [_F, _P]),
     "sgta_topk_index": (_I, [_P, _P, _I, _I, _I, _I, _P]),

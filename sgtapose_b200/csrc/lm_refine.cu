@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <vector>
 
 namespace sgta {
 
@@ -100,12 +101,14 @@ static bool solve7(double A[LM_P][LM_P], double* b) {
 }
 
 // GN (LM.py:220-232) in float64
+// behind_camera_guard: see sgta_lm_refine below (the `LM` symbol runs without it, like the reference binary)
 static int lm_solve(const double* v0, const double* x2d, const double* x3d, const double* w, const double* K, double* ans,
-                    int n) {
-  constexpr int MAXN = 64;
-  if (n <= 0 || n > MAXN) return SGTA_EINVAL;
+                    int n, bool behind_camera_guard) {
+  if (n <= 0) return SGTA_EINVAL;
   const int m = 2 * n + 1;
-  double F[2 * MAXN + 1], J[(2 * MAXN + 1) * LM_P];
+  std::vector<double> Fv((size_t)m), Jv((size_t)m * LM_P);     // any number of correspondences, like the reference
+  double* F = Fv.data();
+  double* J = Jv.data();
   double v[LM_P];
   memcpy(v, v0, sizeof(v));
   double step = 7 * 100.0;                                  // delta = ones * 100
@@ -130,13 +133,14 @@ static int lm_solve(const double* v0, const double* x2d, const double* x3d, cons
     for (int a = 0; a < LM_P; ++a) { v[a] -= g[a]; step += fabs(g[a]); }
     if (!(step == step)) break;                             // NaN: np.sum(abs(delta)) > 1e-4 is False
   }
-  // Defined behaviour where the reference's iteration is chaotic: on some badly started problems the .so ends
-  // in NaN / Inf (and its caller keeps the PnP pose, analysis.py:206-210) while 1e-16 differences in the 7x7
-  // solve can send this iteration to a finite mirror pose instead.  A pose that puts a keypoint behind the
-  // camera is reported as NaN, i.e. through the caller's existing fall-back.
+  // Optional guard (sgta_lm_refine only, a DELIBERATE deviation recorded in include/sgta_b200.h): where the
+  // reference's iteration is chaotic the .so may end in NaN / Inf (and its caller keeps the PnP pose,
+  // analysis.py:206-210) while 1e-16 differences in the 7x7 solve can send this iteration to a finite mirror
+  // pose instead; with the guard a pose that puts a keypoint behind the camera is reported as NaN, i.e. through
+  // the caller's existing fall-back.  Without it the iterate is returned as it is, finite or not.
   bool bad = false;
-  for (int a = 0; a < LM_P; ++a) bad = bad || !isfinite(v[a]);
-  for (int i = 0; i < n && !bad; ++i) {
+  for (int i = 0; i < n && behind_camera_guard && !bad; ++i) {
+    if (!(w[2 * i] != 0.0 || w[2 * i + 1] != 0.0)) continue;   // zero-weight (missing) points do not vote
     const double x = x3d[3 * i], y = x3d[3 * i + 1], z = x3d[3 * i + 2];
     const double a = v[0] * x + v[2] * z - v[3] * y, b = v[0] * y - v[1] * z + v[3] * x, c = v[0] * z + v[1] * y - v[2] * x;
     const double d = -v[1] * x - v[2] * y - v[3] * z;
@@ -153,13 +157,15 @@ using namespace sgta;
 extern "C" int sgta_lm_refine(const double* value_init, const double* x2d, const double* x3d, const double* weights,
                               const double* camera, double* ans, int num_points) {
   SGTA_REQUIRE(value_init && x2d && x3d && weights && camera && ans, "sgta_lm_refine: null pointer");
-  SGTA_REQUIRE(num_points > 0 && num_points <= 64, "sgta_lm_refine: 1..64 correspondences (got %d)", num_points);
-  return lm_solve(value_init, x2d, x3d, weights, camera, ans, num_points);
+  SGTA_REQUIRE(num_points > 0, "sgta_lm_refine: at least one correspondence (got %d)", num_points);
+  return lm_solve(value_init, x2d, x3d, weights, camera, ans, num_points, true);
 }
 
 // the symbol rf_tools/LM.py binds (`so.LM(value_init_l, x2d_input, x3d_input, weightl, cameral, ans, num_points)`)
 extern "C" void LM(double* value_init, double* x2d, double* x3d, double* weights, double* camera, double* ans,
                    int num_points) {
-  if (sgta_lm_refine(value_init, x2d, x3d, weights, camera, ans, num_points) != SGTA_OK)
-    for (int i = 0; i < 7; ++i) ans[i] = NAN;             // the caller falls back to the PnP pose on NaN (analysis.py:208)
+  // bit-faithful to the reference iteration: no behind-the-camera guard, whatever the iterate is comes back
+  if (!value_init || !x2d || !x3d || !weights || !camera || !ans) return;
+  if (lm_solve(value_init, x2d, x3d, weights, camera, ans, num_points, false) != SGTA_OK)
+    for (int i = 0; i < 7; ++i) ans[i] = NAN;             // num_points <= 0
 }

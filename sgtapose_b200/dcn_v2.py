@@ -11,6 +11,13 @@ checkpoints load unchanged (model.py:43-84).
 forward(x: [B,Cin,H,W] fp32 CUDA) -> [B,Cout,Ho,Wo]; differentiable w.r.t. x, weight, bias
 and conv_offset_mask.* through hand-written CUDA kernels (sgta_dcn_forward/backward).
 There is no CPU fallback: a non-CUDA input raises.
+
+Inference route (autograd off, 3x3 / stride 1 / pad 1 / dilation 1 / one deformable group, Cin and Cout multiples
+of 64 -- every DCN of the hot path, dla.py:545): the same tcgen05 kernels as the compiled engine.  The NCHW input
+is packed once into the fp16 hi/lo planes layout (csrc/planes.cuh), conv_offset_mask runs as a shift-GEMM
+(`sgta_planes_conv`), the bilinear gather + implicit GEMM as `sgta_planes_dcn`, and the result is unpacked to NCHW
+fp32.  Everything else (training, other geometries) takes the exact-fp32 SIMT kernels.  `DCN.tensor_core = False`
+turns the route off.
 """
 import math
 
@@ -99,7 +106,44 @@ class DCN(nn.Module):
             self.conv_offset_mask.weight.zero_()
             self.conv_offset_mask.bias.zero_()
 
+    tensor_core = True        # class-wide switch for the inference route
+
+    def _tc_eligible(self, x):
+        return (self.tensor_core and x.is_cuda and not torch.is_grad_enabled() and x.dim() == 4
+                and self.kernel_size == (3, 3) and self.stride == 1 and self.padding == 1 and self.dilation == 1
+                and self.deformable_groups == 1 and self.in_channels % 64 == 0 and self.out_channels % 64 == 0)
+
+    def _tc_forward(self, x):
+        """tcgen05 route: planes in, planes out, same kernels as engine.InferenceEngine._deform_conv."""
+        from . import planes as P
+        dev = x.device
+        B, Cin, H, W = x.shape
+        Cout = self.out_channels
+        params = (self.weight, self.bias, self.conv_offset_mask.weight, self.conv_offset_mask.bias)
+        wkey = tuple((t.data_ptr(), t._version) for t in params) + (str(dev),)
+        cache = self.__dict__.setdefault("_tc_cache", {})
+        if cache.get("wkey") != wkey:
+            ones = lambda n: torch.ones(n, device=dev)
+            cache["om"] = P.ConvSpec(P.weight_matrix(self.conv_offset_mask.weight.detach().float()), ones(27),
+                                     self.conv_offset_mask.bias.detach().float(), Cin, 3, 1, 2)       # N 27 -> 32
+            cache["w"] = P.ConvSpec(P.weight_matrix(self.weight.detach().float()), ones(Cout),
+                                    self.bias.detach().float(), Cin, 3, 1, 2)
+            cache["wkey"] = wkey
+        skey = (B, H, W)
+        if cache.get("skey") != skey:
+            cache["x"] = P.PlaneBuf(B, Cin, H, W, 2, dev)
+            cache["y"] = P.PlaneBuf(B, Cout, H, W, 2, dev)
+            cache["omf"] = torch.zeros(B * (H + 2) * (W + 2) + 256, 32, device=dev, dtype=torch.float32)
+            cache["skey"] = skey
+        xb, yb, w = cache["x"], cache["y"], cache["w"]
+        xb.from_nchw(x)
+        P.conv(cache["om"], xb.full, y_f32=cache["omf"], ld_f32=32, epi=P.EPI_F32ROWS)
+        P.dcn(xb.full, cache["omf"], w, w.scale, w.shift, yb.full, relu=False)
+        return yb.to_nchw()
+
     def forward(self, x):
+        if self._tc_eligible(x):
+            return self._tc_forward(x)
         om = self.conv_offset_mask(x)
         return dcn_v2_conv(x, om, self.weight, self.bias, self.stride, self.padding, self.dilation,
                            self.deformable_groups)

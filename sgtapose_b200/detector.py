@@ -34,17 +34,22 @@ MISSING = -999.999 * 4          # sgta_detector.py:613, :521
 DEFAULT_K = np.array([[502.30, 0.0, 319.75], [0.0, 502.30, 179.75], [0.0, 0.0, 1.0]])   # sgta_detector.py:83
 
 
-def _rotation_from_rvec(rvec):
-    """geometric_vision.py:15-25 convert_rvec_to_quaternion (pyrr Quaternion.from_axis_rotation, normalised)
-    followed by `.matrix33` (:291).  pyrr is an un-pinned, absent dependency: restated from its published
-    formulas (pyrr 0.10.3 quaternion.create_from_axis_rotation / matrix33.create_from_quaternion)."""
+def quaternion_from_rvec(rvec):
+    """geometric_vision.py:15-25 convert_rvec_to_quaternion: axis-angle -> xyzw quaternion
+    (pyrr `Quaternion.from_axis_rotation`, then `.normalize()`).  pyrr is an un-pinned, absent dependency: restated
+    from its published formulas (pyrr 0.10.3 quaternion.create_from_axis_rotation / normalize)."""
     theta = np.sqrt(rvec[0] * rvec[0] + rvec[1] * rvec[1] + rvec[2] * rvec[2])
     axis = np.array([rvec[0] / theta, rvec[1] / theta, rvec[2] / theta], dtype=np.float64)
     half = theta * 0.5
     s = np.sin(half)
-    qx, qy, qz, qw = axis[0] * s, axis[1] * s, axis[2] * s, np.cos(half)
-    n = np.sqrt(qx * qx + qy * qy + qz * qz + qw * qw)
-    qx, qy, qz, qw = qx / n, qy / n, qz / n, qw / n
+    q = np.array([axis[0] * s, axis[1] * s, axis[2] * s, np.cos(half)])
+    q = q / np.sqrt(np.sum(q ** 2))                          # create_from_axis_rotation normalises ...
+    return q / np.sqrt(np.sum(q ** 2))                       # ... and convert_rvec_to_quaternion normalises again
+
+
+def rotation_from_quaternion(q):
+    """pyrr `Quaternion.matrix33` (matrix33.create_from_quaternion) as used at geometric_vision.py:291, :189."""
+    qx, qy, qz, qw = [float(v) for v in q]
     sqw, sqx, sqy, sqz = qw * qw, qx * qx, qy * qy, qz * qz
     inv = 1.0 / (sqx + sqy + sqz + sqw)
     return np.array([
@@ -53,22 +58,50 @@ def _rotation_from_rvec(rvec):
         [2.0 * (qx * qz - qy * qw) * inv, 2.0 * (qy * qz + qx * qw) * inv, (-sqx - sqy + sqz + sqw) * inv]])
 
 
-def solve_pnp(canonical_points, projections, camera_K):
+def _rotation_from_rvec(rvec):
+    return rotation_from_quaternion(quaternion_from_rvec(rvec))
+
+
+def solve_pnp_quat(canonical_points, projections, camera_K):
     """geometric_vision.py:43-116: cv2 EPnP, then ITERATIVE refinement from that guess.
-    -> (ok, translation [3], rotation [3,3])"""
+    -> (ok, translation [3], quaternion xyzw [4]) -- the pose the reference reports (analysis.py:808-880)."""
     import cv2
     pts = np.asarray(canonical_points, np.float64)
     prj = np.asarray(projections, np.float64)
-    if len(pts) == 0 or len(pts) != len(prj):
+    if len(pts) != len(prj):
+        raise AssertionError("Expected canonical_points and projections to have the same length, but they are "
+                             "length {} and {}.".format(len(pts), len(prj)))          # geometric_vision.py:54-58
+    if len(pts) == 0:
         return False, None, None
     try:
         ok, rvec, tvec = cv2.solvePnP(pts.reshape(-1, 1, 3), prj.reshape(-1, 1, 2), camera_K, np.array([]),
                                       flags=cv2.SOLVEPNP_EPNP)
         ok, rvec, tvec = cv2.solvePnP(pts.reshape(-1, 1, 3), prj.reshape(-1, 1, 2), camera_K, np.array([]),
                                       flags=cv2.SOLVEPNP_ITERATIVE, useExtrinsicGuess=True, rvec=rvec, tvec=tvec)
-        return bool(ok), tvec[:, 0], _rotation_from_rvec(rvec[:, 0])
+        return bool(ok), tvec[:, 0], quaternion_from_rvec(rvec[:, 0])
     except Exception:                       # the reference swallows solver failures the same way (:111-114)
         return False, None, None
+
+
+def solve_pnp(canonical_points, projections, camera_K):
+    """-> (ok, translation [3], rotation [3,3]); see solve_pnp_quat."""
+    ok, t, q = solve_pnp_quat(canonical_points, projections, camera_K)
+    return (ok, t, rotation_from_quaternion(q)) if ok else (False, None, None)
+
+
+def post_process_batch(scores, cts_wreg, trans_inv, out_thresh):
+    """post_process (sgta_detector.py:929-942 -> post_process.py:93-117), merge_outputs (:955-961) and
+    _get_final_kps (:608-651, is_ct branch) for a whole batch: the best-scoring detection of every class, in
+    raw-image pixels; MISSING where nothing passed `out_thresh`.  scores [B,K], cts_wreg [B,K,2] float32;
+    trans_inv: the float32 inverse output affine (post_process.py:102-103)."""
+    B, K = scores.shape
+    ones = np.ones((B * K, 3), np.float32)
+    ones[:, :2] = cts_wreg.reshape(-1, 2)
+    raw = np.dot(trans_inv, ones.transpose()).transpose()[:, :2].reshape(B, K, 2)   # image.py:20-26
+    keep = (scores >= out_thresh) & (scores > out_thresh)
+    out = np.full((B, K, 2), MISSING)
+    out[keep] = raw[keep]
+    return out
 
 
 def is_pnp(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K):
@@ -132,16 +165,7 @@ class LockstepDetector:
         return is_pnp(x3d_prev[good], kps[good], x3d_next, kps, self.K)
 
     def _post(self, scores, cts_wreg):
-        """post_process (:929-942 -> post_process.py:93-117), merge_outputs (:955-961) and _get_final_kps
-        (:608-651) for the whole batch: the best-scoring detection of every class, in raw-image pixels."""
-        B, K = scores.shape
-        ones = np.ones((B * K, 3), np.float32)
-        ones[:, :2] = cts_wreg.reshape(-1, 2)
-        raw = np.dot(self.trans_inv, ones.transpose()).transpose()[:, :2].reshape(B, K, 2)   # image.py:20-26
-        keep = (scores >= self.out_thresh) & (scores > self.out_thresh)
-        out = np.full((B, K, 2), MISSING)
-        out[keep] = raw[keep]
-        return out
+        return post_process_batch(scores, cts_wreg, self.trans_inv, self.out_thresh)
 
     # ------------------------------------------------------------------ one frame of every clip
     def step(self, images, x3d_prev=None, x3d_next=None):
@@ -251,13 +275,14 @@ class ClipGroups:
         bench plant detections there).  Returns per-frame {'kps_raw' [B,n_kp,2], 'scores' [B,n_kp]}."""
         G = len(self.dets)
         out = [dict() for _ in range(n_frames)]
+        self.reset()                                   # a reused detector starts its clips again at frame 0
 
         def begin(g, f):
             d = self.dets[g]
             if before_begin is not None:
                 before_begin(g, f, d)
-            prev = self._slice(x3d_fn(f - 1), g) if (x3d_fn is not None and d.frame > 0) else None
-            nxt = self._slice(x3d_fn(f), g) if (x3d_fn is not None and d.frame > 0) else None
+            prev = self._slice(x3d_fn(f - 1), g) if (x3d_fn is not None and f > 0) else None
+            nxt = self._slice(x3d_fn(f), g) if (x3d_fn is not None and f > 0) else None
             d.begin(self._slice(images_fn(f), g), prev, nxt)
 
         def finish(g, f):

@@ -399,28 +399,62 @@ def create_model(arch, head, head_conv, opt=None):
     return _network_factory[name](num_layers, heads=head, head_convs=head_conv, opt=opt)
 
 
-def load_model(model, model_path, opt=None):
-    """Tolerant checkpoint load (model.py:43-103 without the optimizer branch): strips a
-    leading `module.`, keeps the model's own tensor on shape mismatch / missing key."""
+def load_model(model, model_path, opt=None, optimizer=None):
+    """Tolerant checkpoint load, same call forms and return values as model.py:43-103: strips a leading `module.`;
+    on a shape mismatch (or `opt.reset_hm` for 80- / 1-class `hm*` tensors) either re-uses the leading slice
+    (`opt.reuse_hm`) or keeps the model's own tensor; missing keys keep their init.  With an optimizer the result
+    is `(model, optimizer, start_epoch)` and, under `opt.resume`, the learning rate is stepped down by 0.1 for
+    every `opt.lr_step` already passed (the reference does not restore the optimizer state either, :86)."""
+    start_epoch = 0
     ckpt = torch.load(model_path, map_location="cpu")
     src = ckpt.get("state_dict", ckpt)
     src = {(k[7:] if k.startswith("module") and not k.startswith("module_list") else k): v
            for k, v in src.items()}
     own = model.state_dict()
+    reset_hm, reuse_hm = bool(getattr(opt, "reset_hm", False)), bool(getattr(opt, "reuse_hm", False))
     merged = {}
-    for k, v in own.items():
-        if k in src and src[k].shape == v.shape:
-            merged[k] = src[k]
+    for k, v in src.items():
+        if k not in own:
+            print("Drop parameter {}.".format(k))
+            continue
+        if v.shape != own[k].shape or (reset_hm and k.startswith("hm") and v.shape[0] in (80, 1)):
+            if reuse_hm and v.dim() == own[k].dim() and v.shape[1:] == own[k].shape[1:]:
+                print("Reusing parameter {}, required shape{}, loaded shape{}.".format(k, own[k].shape, v.shape))
+                t = own[k].clone()
+                n = min(t.shape[0], v.shape[0])
+                t[:n] = v[:n]
+                merged[k] = t
+            else:
+                print("Skip loading parameter {}, required shape{}, loaded shape{}.".format(k, own[k].shape, v.shape))
+                merged[k] = own[k]
         else:
-            print("No param / shape mismatch, keeping init: %s" % k)
+            merged[k] = v
+    for k, v in own.items():
+        if k not in merged:
+            print("No param {}.".format(k))
             merged[k] = v
     model.load_state_dict(merged, strict=False)
+    if optimizer is not None and getattr(opt, "resume", False):
+        if "optimizer" in ckpt:
+            start_epoch = ckpt["epoch"]
+            start_lr = opt.lr
+            for step in opt.lr_step:
+                if start_epoch >= step:
+                    start_lr *= 0.1
+            for group in optimizer.param_groups:
+                group["lr"] = start_lr
+            print("Resumed optimizer with start lr", start_lr)
+        else:
+            print("No optimizer parameters in checkpoint.")
+    if optimizer is not None:
+        return model, optimizer, start_epoch
     return model
 
 
 def save_model(path, epoch, model, optimizer=None):
     """model.py:105-114."""
-    data = {"epoch": epoch, "state_dict": model.state_dict()}
+    wrapped = isinstance(model, (torch.nn.DataParallel, torch.nn.parallel.DistributedDataParallel))
+    data = {"epoch": epoch, "state_dict": (model.module if wrapped else model).state_dict()}
     if optimizer is not None:
         data["optimizer"] = optimizer.state_dict()
     torch.save(data, path)

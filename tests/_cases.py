@@ -90,3 +90,79 @@ def prior_maps_for_index_cases():
     m[1] = rng.random((7, 96, 96), dtype=np.float32)
     # sample 2 stays all-zero: frame-0 behaviour (every top-1 index is 0)
     return m
+
+
+# ----------------------------------------------------------------------------- host PnP / pose / metrics cases
+MISSING = -999.999 * 4
+CAMERA_K = np.array([[502.30, 0.0, 319.75], [0.0, 502.30, 179.75], [0.0, 0.0, 1.0]])    # sgta_detector.py:83
+RAW_W, RAW_H = 640, 360
+
+
+def panda_scene(rng, n):
+    """[n,7,3] Panda-like keypoint positions in front of the camera (metres, camera frame)."""
+    return rng.uniform([-0.35, -0.2, 1.2], [0.35, 0.2, 1.8], size=(n, 7, 3))
+
+
+def project(x3d, K=CAMERA_K):
+    p = np.einsum("ij,...j->...i", K, x3d)
+    return p[..., :2] / p[..., 2:]
+
+
+def pnp_cases():
+    """(prev_pos [7,3], detected kps [7,2] with MISSING rows, next_pos [7,3]) of geometric_vision.is_pnp."""
+    rng = np.random.default_rng(41)
+    cases = []
+    for i in range(8):
+        prev = panda_scene(rng, 1)[0]
+        nxt = prev + rng.normal(0, 0.004, size=prev.shape)
+        kps = project(prev) + rng.normal(0, [0.0, 0.3, 1.0, 3.0][i % 4], size=(7, 2))
+        if i in (2, 5):
+            kps[[1, 4]] = MISSING
+        if i == 6:
+            kps[[0, 1, 2]] = MISSING                  # four detections left: the EPnP minimum
+        if i == 7:
+            kps[[0, 1, 2, 3, 5]] = MISSING            # two detections: cv2 raises, the reference swallows it
+        cases.append((prev, kps, nxt))
+    return cases
+
+
+def pose_heatmap_cases(n=12, q=96):
+    """Synthetic head outputs whose blobs sit at the projections of a known scene:
+    hm [n,7,q,q] (post-sigmoid range), reg, tracking [n,2,q,q], x3d [n,7,3] = the keypoints in the ROBOT frame
+    (a random rigid transform away from the camera frame, so the recovered pose is a real rotation + translation)."""
+    import cv2
+    from sgtapose_b200 import priors as PR
+    rng = np.random.default_rng(43)
+    x3d_cam = panda_scene(rng, n)
+    x3d = np.empty_like(x3d_cam)
+    for i in range(n):
+        R0 = cv2.Rodrigues(rng.normal(0, 0.9, size=3))[0]
+        t0 = rng.uniform([-0.2, -0.2, 0.8], [0.2, 0.2, 1.4])
+        x3d[i] = (x3d_cam[i] - t0) @ R0                       # rows: R0^T (x_cam - t0)
+    c = np.array([RAW_W / 2.0, RAW_H / 2.0], dtype=np.float32)
+    trans_out = PR.get_affine_transform(c, max(RAW_H, RAW_W) * 1.0, 0, [q, q])
+    raw = project(x3d_cam)
+    ctr = np.einsum("ij,nkj->nki", trans_out, np.concatenate([raw, np.ones((n, 7, 1))], 2))
+    yy, xx = np.mgrid[0:q, 0:q].astype(np.float32)
+    hm = rng.random((n, 7, q, q), dtype=np.float32) * np.float32(0.004)
+    for i in range(n):
+        for k in range(7):
+            if i % 5 == 4 and k == i % 7:
+                continue                                # a keypoint the network missed
+            cx, cy = ctr[i, k]
+            hm[i, k] += (0.9 * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 8.0)).astype(np.float32)
+    reg = (rng.random((n, 2, q, q), dtype=np.float32) * np.float32(0.8)).astype(np.float32)
+    trk = rng.normal(0, 1.5, size=(n, 2, q, q)).astype(np.float32)
+    return np.clip(hm, 0, 1), reg, trk, x3d
+
+
+def metrics_case():
+    rng = np.random.default_rng(47)
+    n = 400
+    gt = rng.uniform([-60, -40], [700, 400], size=(n, 2))
+    det = gt + rng.normal(0, 4.0, size=(n, 2))
+    det[rng.random(n) < 0.15] = MISSING
+    add = np.abs(rng.normal(0.02, 0.02, size=150))
+    add[rng.random(150) < 0.1] = -999.99
+    inframe = rng.integers(2, 8, size=150)
+    return det, gt, add, inframe

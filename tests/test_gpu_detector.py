@@ -42,7 +42,8 @@ def test_post_process_matches_reference_loops(det):
 
 def test_step_sequence_priors_and_decode(det):
     """Three frames of three clips.  Every frame: (1) the prior maps the runner rendered into the engine's
-    input buffers == the reference's host rendering from the SAME detections (bit-exact); (2) the
+    input buffers == the oracle's host rendering from the SAME detections, through the ORACLE's own PnP front-end
+    (oracle/detector.py::is_pnp, pinned to the reference in tests/golden/pnp.npz), bit-exact; (2) the
     detections it reports == reference post-processing of the oracle's decode of the engine's heads."""
     from sgtapose_b200 import detector, synth
     rng = np.random.default_rng(2)
@@ -68,7 +69,7 @@ def test_step_sequence_priors_and_decode(det):
                 want = (np.zeros((S, S), np.float32),) * 2 + (np.zeros((7, q, q), np.float32),) * 2
             else:
                 want = odet.further_inputs(before[b], x3d[f - 1][b], x3d[f][b], det.K, det.trans_input,
-                                           det.trans_output, S, q, det.raw_w, det.raw_h, detector.is_pnp)
+                                           det.trans_output, S, q, det.raw_w, det.raw_h)
             got = (inp["pre_hm"][b, 0], inp["repro_hm"][b, 0], inp["pre_hm_cls"][b], inp["repro_hm_cls"][b])
             for name, g, w in zip(("pre_hm", "repro_hm", "pre_hm_cls", "repro_hm_cls"), got, want):
                 assert np.array_equal(g.cpu().numpy(), w), (f, b, name)
