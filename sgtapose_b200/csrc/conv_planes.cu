@@ -42,7 +42,7 @@ template <int PROD> struct GProd { static constexpr int warps = PROD == 0 ? 16 :
 template <int PROD> struct GThreads { static constexpr int value = (GProd<PROD>::warps + 2 + 4) * 32; };   // + B loader, MMA, 4 epilogue warps
 constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
                                                          // each, tests/cuda/tma_bw_probe.cu): spread them over 4
-constexpr int S_EPI_NH = 1;                              // epilogue warps per TMEM lane quadrant
+constexpr int S_EPI_NH = 2;                              // epilogue warps per TMEM lane quadrant (each takes half the columns)
 constexpr int S_THREADS = (S_TMA_WARPS + 1 + 4 * S_EPI_NH) * 32;    // TMA warps, MMA, epilogue warps
 
 enum { PROD_DCN = 0, PROD_STRIDE = 1, PROD_SMALLC = 2 };
@@ -64,6 +64,7 @@ struct ConvP {
   int act, epi, tmem_cols;
   int acc_r;             // D0 accumulators per stage (k steps rotate over them: shorter fp32 chains)
   int acc_stages;        // TMEM accumulator stages (2 = epilogue overlaps the next tile)
+  int nslots, nd1;       // fp32 mode: D0 band slots (2..6) and D1 buffers (1..2) in TMEM, NT columns each
   int stride;
   int in_Wp, in_Hp;      // input frame (gather kernels)
   int seg_groups;        // SMALLC: 16-byte groups per segment (8 or 4)
@@ -140,6 +141,38 @@ __device__ __forceinline__ void issue_band(uint32_t a_base, uint32_t a_plane, co
   for (int dx = 0; dx < TAPS; ++dx) {
     if (dx == 0) issue_kblock<NS, FIRST, R>(a_base, a_plane, b_addr[0], b_plane, tacc, NT, idesc, rb);
     else issue_kblock<NS, false, R>(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tacc, NT, idesc, rb + dx);
+    mma_commit(b_rel[dx]);
+  }
+  mma_commit(a_rel);
+}
+
+// ---- fp32 mode (NS = 2), band-drain accumulation.  The tensor core truncates every time it adds a K = 16 dot
+// product into the fp32 accumulator (~1 ulp per add, biased towards zero), so a K = 4608 chain loses ~1e-5 -- ten
+// times what an FFMA loop loses, and the synthetic network amplifies it.  Here a D0 (hi*hi) accumulator only ever
+// sums ONE band of 12 K steps; the epilogue warps, idle during the main loop anyway, pull every finished band out
+// of TMEM and add it to their registers in round-to-nearest fp32 while the MMA warp fills the other D0 slot.  D1
+// (hi*lo + lo*hi, scaled 2^-11) runs over the whole tile: its truncation is 2^-11 times smaller.
+// TMEM columns: [D0 slot 0 | D0 slot 1 | D1 of even tiles | D1 of odd tiles], NT each.
+constexpr int BAND_KSTEPS = 12;
+__device__ __forceinline__ void issue_kblock_f32(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
+                                                 uint32_t tD0, uint32_t tD1, uint32_t idesc, uint32_t acc0, uint32_t acc1) {
+  const uint64_t ah = smem_desc_sw128(a_addr), bh = smem_desc_sw128(b_addr);
+  const uint64_t al = smem_desc_sw128(a_addr + a_plane), bl = smem_desc_sw128(b_addr + b_plane);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    mma_bf16_ss(tD0, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, k == 0 ? acc0 : 1u);
+    mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, k == 0 ? acc1 : 1u);
+    mma_bf16_ss(tD1, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
+  }
+}
+template <int TAPS>
+__device__ __forceinline__ void issue_band_f32(uint32_t a_base, uint32_t a_plane, const uint32_t (&b_addr)[3], uint32_t b_plane,
+                                               uint32_t tD0, uint32_t tD1, uint32_t idesc, uint32_t acc0, uint32_t acc1,
+                                               uint64_t* const (&b_rel)[3], uint64_t* a_rel) {
+#pragma unroll
+  for (int dx = 0; dx < TAPS; ++dx) {
+    issue_kblock_f32(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tD0, tD1, idesc, dx == 0 ? acc0 : 1u,
+                     dx == 0 ? acc1 : 1u);
     mma_commit(b_rel[dx]);
   }
   mma_commit(a_rel);
@@ -307,6 +340,111 @@ __device__ __forceinline__ void epilogue_group(const ConvP& p, const EpiRow& e, 
   epi_finish<NS>(p, e, n, o);
 }
 
+// ---- fp32 band-drain epilogue (see issue_kblock_f32): one thread = one output row (TMEM lane) and NG 16-column
+// groups of it, starting at group g0 (NH epilogue warps per lane quadrant split the columns between them)
+struct Ring {
+  uint32_t i, ph;
+  int n;
+  __device__ __forceinline__ void next() { if ((int)++i == n) { i = 0; ph ^= 1u; } }
+};
+__device__ __forceinline__ void epi_row_setup(const ConvP& p, int m, EpiRow& e) {
+  e.m = m;
+  decode_row(p, e.m, e.px, e.py, e.b);
+  e.inP = e.m < p.P;
+  e.valid = e.inP && e.px >= 1 && e.px <= p.Wo && e.py >= 1 && e.py <= p.Ho;
+  const bool pl_like = p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC;
+  e.has_res = pl_like && e.valid && p.res.base != nullptr;
+  e.staged = false;
+  e.srow = 0; e.sxor = 0;
+}
+template <int NG, int NH, bool BACKOFF>
+__device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem, int total, int nbands, int q, int half,
+                                                   int lane, uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty) {
+  const int NT = p.NT, g0 = half * NG;
+  const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+  Ring rs{0u, 0u, p.nslots}, rd{0u, 0u, p.nd1};
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+    float acc[NG][16];
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[g][j] = 0.f;
+    for (int bnd = 0; bnd < nbands; ++bnd) {
+      if (BACKOFF) mbar_wait_backoff(&slot_full[rs.i], rs.ph);
+      else mbar_wait(&slot_full[rs.i], rs.ph);
+      tc_fence_after();
+      if (!(p.dbg & 4)) {
+        const uint32_t ts = lane_base + rs.i * (uint32_t)NT;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if ((g0 + g) * 16 < NT) {
+            uint32_t d[16];
+            tmem_ld16(ts + (uint32_t)((g0 + g) * 16), d);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[g][j] += __uint_as_float(d[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_empty[rs.i]);
+      rs.next();
+    }
+    if (!(p.dbg & 4)) {
+      const uint32_t td = lane_base + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if ((g0 + g) * 16 < NT) {
+          uint32_t d[16];
+          tmem_ld16(td + (uint32_t)((g0 + g) * 16), d);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[g][j] = fmaf(__uint_as_float(d[j]), LO_INV, acc[g][j]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&d1_empty[rd.i]);
+    rd.next();
+    if (p.dbg & 4) continue;
+    EpiRow e;
+    epi_row_setup(p, m0 + q * 32 + lane, e);
+    if (p.epi == SGTA_EPI_STEM) {
+      // N = 32: out[c] = relu(bn_a(acc[c])) + relu(bn_b(acc[16+c])), c < 16   (dla.py:325-331); NH = 1 here
+      if (NG >= 2 && e.valid) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float va = fmaf(acc[0][j], __ldg(p.scale + j), __ldg(p.shift + j));
+          const float vb = fmaf(acc[NG >= 2 ? 1 : 0][j], __ldg(p.scale + 16 + j), __ldg(p.shift + 16 + j));
+          o[j] = fmaxf(va, 0.f) + fmaxf(vb, 0.f);
+        }
+        float lo8[8], hi8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo8[j] = o[j]; hi8[j] = o[8 + j]; }
+        sc_store8<2>(p.y, e.m, 0, lo8);
+        sc_store8<2>(p.y, e.m, 8, hi8);
+      }
+      continue;
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+      if ((g0 + g) * 16 < NT) epi_finish<2>(p, e, nt * NT + (g0 + g) * 16, acc[g]);
+  }
+}
+template <int NH, bool BACKOFF>
+__device__ __forceinline__ void fp32_epilogue(const ConvP& p, uint32_t tmem, int total, int nbands, int q, int half, int lane,
+                                              uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty) {
+  const int per = ((p.NT + 15) / 16 + NH - 1) / NH;          // 16-column groups per thread
+  if (per <= 1) fp32_epilogue_loop<1, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
+  else if (per <= 2) fp32_epilogue_loop<2, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
+  else if (per <= 4 || NH > 1) fp32_epilogue_loop<4, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
+  else if constexpr (NH == 1) fp32_epilogue_loop<8, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
+}
+
 // NH epilogue warps per lane quadrant; `half` in [0, NH) is this warp's share
 template <int NS, int NH>
 __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row, uint32_t stage_s,
@@ -414,11 +552,13 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   uint64_t *a_full = bars, *a_empty = bars + 8, *b_full = bars + 16, *b_empty = bars + 24;
   uint64_t *acc_full = bars + 32, *acc_empty = bars + 34;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+  uint64_t *slot_full = bars + 38, *slot_empty = bars + 44;     // fp32 mode: up to 6 D0 band slots (acc_empty = D1 buffers)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], NS); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * S_EPI_NH); }
+    for (int s = 0; s < 6; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4 * S_EPI_NH); }
     fence_mbar_init();
   }
   if (warp == S_TMA_WARPS) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
@@ -483,12 +623,21 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     int st = 0, sb = 0;
     uint32_t aph = 0, bph = 0;             // parity to wait for on the *_full barriers
     uint32_t as = 0, accph = 1;            // accumulator stage and parity of its acc_empty barrier
+    Ring rs{0u, 1u, p.nslots}, rd{0u, 1u, p.nd1};   // fp32 mode: D0 band slots / D1 buffers (parity of their *_empty)
     const uint32_t a_smem = smem_u32(sA), b_smem = smem_u32(sB);
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int m0 = (t / p.n_tiles) * TM;
-      mbar_wait(&acc_empty[as], accph);
-      const uint32_t tacc = tmem + as * acc_stride;
+      uint32_t tacc = 0, tD0 = 0, tD1 = 0, sl = 0;
+      if constexpr (NS == 2) {
+        mbar_wait(&acc_empty[rd.i], rd.ph);                          // the epilogue has read this D1 buffer
+        tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+        rd.next();
+      } else {
+        mbar_wait(&acc_empty[as], accph);
+        tacc = tmem + as * acc_stride;
+      }
       int rb = 0;                          // 1x1: K step rotation start (3x3 bands advance by 12 = 0 mod 3)
+      int ks = 0;                          // fp32 mode: K steps already in the open D0 slot
       bool first = true;
       for (int kc = 0; kc < p.KC; ++kc) {
         for (int band = 0; band < nb; ++band) {
@@ -510,45 +659,75 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
               b_rel[dx] = &b_empty[0];
             }
           }
-          tc_fence_after();
-          if (elect_one()) {
-            if (ntap_b == 3) {
-              if (first) issue_band<NS, true, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
-              else issue_band<NS, false, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
-            } else {
-              if (first) issue_band<NS, true, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
-              else issue_band<NS, false, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb, b_rel, &a_empty[st]);
+          if constexpr (NS == 2) {
+            if (ks == 0) {
+              sl = rs.i;
+              mbar_wait(&slot_empty[sl], rs.ph);                      // the epilogue has drained this D0 slot
+              tD0 = tmem + sl * (uint32_t)NT;
+              rs.next();
             }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t acc0 = ks ? 1u : 0u, acc1 = first ? 0u : 1u;
+              if (ntap_b == 3) issue_band_f32<3>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
+              else issue_band_f32<1>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
+            }
+            __syncwarp();
+            ks += ntap_b * 4;
+            const bool last = kc == p.KC - 1 && band == nb - 1;
+            if (ks >= BAND_KSTEPS || last) {
+              if (elect_one()) mma_commit(&slot_full[sl]);
+              __syncwarp();
+              ks = 0;
+            }
+          } else {
+            tc_fence_after();
+            if (elect_one()) {
+              if (ntap_b == 3) {
+                if (first) issue_band<NS, true, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+                else issue_band<NS, false, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+              } else {
+                if (first) issue_band<NS, true, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+                else issue_band<NS, false, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb, b_rel, &a_empty[st]);
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
           first = false;
           if (R == 3 && ntap_b == 1) rb = rb == 2 ? 0 : rb + 1;
           if (++st == p.SA) { st = 0; aph ^= 1u; }
         }
       }
-      if (elect_one()) mma_commit(&acc_full[as]);
-      __syncwarp();
-      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+      if constexpr (NS != 2) {
+        if (elect_one()) mma_commit(&acc_full[as]);
+        __syncwarp();
+        if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3, half = (warp - (S_TMA_WARPS + 1)) >> 2;
-    // the tile releases its accumulators itself, right after reading them (see epilogue_tile)
-    const bool early = NS == 2 && S_EPI_NH == 1 && p.acc_stages == 1 && NT == 128 && p.stg_bytes == 0 && p.epi != SGTA_EPI_STEM;
-    uint32_t as = 0, accph = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      mbar_wait_backoff(&acc_full[as], accph);
-      tc_fence_after();
-      if (!(p.dbg & 4))
-        epilogue_tile<NS, S_EPI_NH>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
-                                    p.stg_bytes ? smem_u32(smem) : 0u, half, early ? &acc_empty[as] : nullptr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0 && !(early && !(p.dbg & 4))) mbar_arrive(&acc_empty[as]);
-      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+    if constexpr (NS == 2) {
+      // fp32 mode: drain every finished band into registers, then D1, then math + stores (under the next tile's MMAs)
+      const int steps = p.KC * nb;                              // issue_band calls per tile, ntap_b * 4 K steps each
+      const int per = BAND_KSTEPS / (ntap_b * 4);               // ... per D0 band: 1 (3x3) or 3 (1x1)
+      fp32_epilogue<S_EPI_NH, false>(p, tmem, total, (steps + per - 1) / per, q, half, lane, slot_full, slot_empty, acc_empty);
+    } else {
+      uint32_t as = 0, accph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+        mbar_wait_backoff(&acc_full[as], accph);
+        tc_fence_after();
+        if (!(p.dbg & 4))
+          epilogue_tile<NS, S_EPI_NH>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
+                                      p.stg_bytes ? smem_u32(smem) : 0u, half, nullptr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+      }
+      if (q == 0 && half == 0 && lane == 0) bulk_wait_all0();
     }
-    if (q == 0 && half == 0 && lane == 0) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -573,13 +752,15 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
   uint64_t *full = bars, *empty = bars + 8, *acc_full = bars + 16, *acc_empty = bars + 18;
   uint64_t* b_ready = bars + 21;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 32);      // DCN sampling table (9*128*32 B)
+  uint64_t *slot_full = bars + 22, *slot_empty = bars + 28;              // fp32 mode: up to 6 D0 band slots (acc_empty = D1 buffers)
+  unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 48);      // DCN sampling table (9*128*32 B)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&full[s], G_PROD_WARPS + (p.b_resident ? 0 : 1)); mbar_init(&empty[s], 1); }
     mbar_init(b_ready, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 6; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4); }
     fence_mbar_init();
   }
   if (warp == G_PROD_WARPS + 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
@@ -867,53 +1048,86 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
     // ==================================================================== MMA issuer
     const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
     constexpr int R = AccR<NS>::value;
+    constexpr int BAND_KB = BAND_KSTEPS / 4;                 // fp32 mode: K blocks per D0 band
     int s = 0;
     uint32_t ph = 0, as = 0, accph = 1;
+    Ring rs{0u, 1u, p.nslots}, rd{0u, 1u, p.nd1};
     const uint32_t smem0 = smem_u32(ring), bres0 = smem_u32(sBres);
     if (p.b_resident) mbar_wait(b_ready, 0);
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      mbar_wait(&acc_empty[as], accph);
-      const uint32_t tacc = tmem + as * acc_stride;
-      int rb = 0, kc = 0, tap = 0;
+      uint32_t tacc = 0, tD0 = 0, tD1 = 0, sl = 0;
+      if constexpr (NS == 2) {
+        mbar_wait(&acc_empty[rd.i], rd.ph);
+        tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+        rd.next();
+      } else {
+        mbar_wait(&acc_empty[as], accph);
+        tacc = tmem + as * acc_stride;
+      }
+      int rb = 0, kc = 0, tap = 0, kin = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[s], ph);
-        tc_fence_after();
         const uint32_t a0 = smem0 + (uint32_t)s * stage_bytes;
         const int blk = PROD == PROD_SMALLC ? kb : tap * p.KC + kc;
         const uint32_t b0 = p.b_resident ? bres0 + (uint32_t)blk * b_bytes : a0 + a_bytes;
         if (++tap == 9) { tap = 0; ++kc; }
-        if (elect_one()) {
-          if (!(p.dbg & 16)) {
-            if (kb == 0) issue_kblock<NS, true>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, 0);
-            else issue_kblock<NS, false>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, rb);
+        if constexpr (NS == 2) {
+          if (kin == 0) {
+            sl = rs.i;
+            mbar_wait(&slot_empty[sl], rs.ph);
+            tD0 = tmem + sl * (uint32_t)NT;
+            rs.next();
           }
-          mma_commit(&empty[s]);
+          tc_fence_after();
+          if (elect_one()) {
+            if (!(p.dbg & 16)) issue_kblock_f32(a0, a_plane, b0, b_plane, tD0, tD1, idesc, kin ? 1u : 0u, kb ? 1u : 0u);
+            mma_commit(&empty[s]);
+            if (kin + 1 == BAND_KB || kb == nkb - 1) mma_commit(&slot_full[sl]);
+          }
+          __syncwarp();
+          if (++kin == BAND_KB || kb == nkb - 1) kin = 0;
+        } else {
+          tc_fence_after();
+          if (elect_one()) {
+            if (!(p.dbg & 16)) {
+              if (kb == 0) issue_kblock<NS, true>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, 0);
+              else issue_kblock<NS, false>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, rb);
+            }
+            mma_commit(&empty[s]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (R == 3) rb = rb == 2 ? 0 : rb + 1;
         if (++s == p.SA) { s = 0; ph ^= 1u; }
       }
-      if (elect_one()) mma_commit(&acc_full[as]);
-      __syncwarp();
-      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+      if constexpr (NS != 2) {
+        if (elect_one()) mma_commit(&acc_full[as]);
+        __syncwarp();
+        if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+      }
     }
   } else {
     // ==================================================================== epilogue warps
     const int q = warp & 3;
-    uint32_t as = 0, accph = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-      mbar_wait_backoff(&acc_full[as], accph);
-      tc_fence_after();
-      if (!(p.dbg & 4))
-        epilogue_tile<NS, 1>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
-                             p.stg_bytes ? smem_u32(smem) : 0u, 0, nullptr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
-      if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+    if constexpr (NS == 2) {
+      constexpr int BAND_KB = BAND_KSTEPS / 4;
+      fp32_epilogue<1, true>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane, slot_full, slot_empty, acc_empty);
+    } else {
+      uint32_t as = 0, accph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+        mbar_wait_backoff(&acc_full[as], accph);
+        tc_fence_after();
+        if (!(p.dbg & 4))
+          epilogue_tile<NS, 1>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
+                               p.stg_bytes ? smem_u32(smem) : 0u, 0, nullptr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
+      }
+      if (q == 0 && lane == 0) bulk_wait_all0();
     }
-    if (q == 0 && lane == 0) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -959,10 +1173,20 @@ static int pick_ntile(int Cout, int NS) {
 // stays below 4e-6 relative without rotation, and R = 1 lets a 128-wide N tile keep TWO accumulator
 // stages so the epilogue overlaps the next tile's MMAs (the 64 -> 768 head convolution)
 static void plan_acc(ConvP& p, int NS, bool short_k = false) {
-  p.acc_r = NS == 2 ? (short_k ? 1 : 3) : 1;   // (3 + 1) * 128 columns still fit the 512 of TMEM
-  const int per_stage = (p.acc_r + NS - 1) * p.NT;
-  p.acc_stages = 2 * per_stage <= 512 ? 2 : 1;
-  int need = p.acc_stages * per_stage, c = 32;
+  (void)short_k;
+  p.acc_r = 1;
+  p.acc_stages = 2;
+  int need = 2 * p.NT;
+  if (NS == 2) {
+    // fp32 mode (band-drain accumulation): D0 band slots + D1 buffers, NT <= 128 columns each.  The MMA warp can
+    // run as many bands ahead of the epilogue warps as there are slots, which is what hides the previous tile's
+    // scale / activation / store phase: as many as the 512 columns give (3 + 1 for 128-wide tiles, 6 + 2 below)
+    const int units = 512 / p.NT;
+    p.nd1 = units >= 8 ? 2 : 1;
+    p.nslots = units - p.nd1 > 6 ? 6 : units - p.nd1;
+    need = (p.nslots + p.nd1) * p.NT;
+  }
+  int c = 32;
   while (c < need) c <<= 1;
   p.tmem_cols = c;
 }
@@ -994,13 +1218,8 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
-  if (p.acc_r == 1) {
-    cudaFuncSetAttribute(conv_shift_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_shift_kernel<NS, 1><<<grid, S_THREADS, smem, st>>>(p);
-  } else {
-    cudaFuncSetAttribute(conv_shift_kernel<NS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_shift_kernel<NS, 3><<<grid, S_THREADS, smem, st>>>(p);
-  }
+  cudaFuncSetAttribute(conv_shift_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  conv_shift_kernel<NS, 1><<<grid, S_THREADS, smem, st>>>(p);
   return check_launch("conv_shift_kernel");
 }
 

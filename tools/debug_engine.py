@@ -8,7 +8,11 @@ from sgtapose_b200 import config, engine, networks, synth
 
 DEV = "cuda"
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+SEED = int(sys.argv[2]) if len(sys.argv) > 2 else 317
+MODES = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fp32", "bf16"]
 B = 2
+from sgtapose_b200 import dcn_v2
+dcn_v2.DCN.tensor_core = False          # the eager tree is the exact-fp32 side of the comparison
 
 
 def rel(a, b):
@@ -18,10 +22,10 @@ def rel(a, b):
 
 opt = config.default_opt()
 m = networks.create_model(config.ARCH, dict(config.HEADS), dict(config.HEAD_CONV), opt).eval()
-sd = synth.synthetic_state_dict(m.state_dict(), seed=317)
+sd = synth.synthetic_state_dict(m.state_dict(), seed=SEED)
 m.load_state_dict(sd)
 m = m.to(DEV)
-ins = [t.to(DEV) for t in synth.synthetic_inputs(B, S, seed=317, frame=1)]
+ins = [t.to(DEV) for t in synth.synthetic_inputs(B, S, seed=SEED, frame=1)]
 cap = {}
 
 
@@ -57,7 +61,7 @@ m.fuse_level = fuse
 with torch.no_grad():
     out = m(*ins)[0]
 
-for mode in ("fp32", "bf16"):
+for mode in MODES:
     eng = engine.InferenceEngine(sd, opt, batch=B, size=S, mode=mode, device=DEV, use_graph=False)
     eo = eng(*ins)[0]
     torch.cuda.synchronize()
@@ -76,10 +80,13 @@ for mode in ("fp32", "bf16"):
         print("%s %.3e" % (key, rel(nchw(eng.buf[key]), cap[key][0])))
     for k in ("hm", "reg", "tracking"):
         print(k, "%.3e" % rel(eo[k], out[k]))
-    if S == 128:
+    gname = "model_S128.npz" if (S == 128 and SEED == 317) else "model_S%d_seed%d.npz" % (S, SEED)
+    gpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", gname)
+    if os.path.exists(gpath):
         import numpy as np
-        g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "model_S128.npz"))
+        g = np.load(gpath)
         for k in ("hm", "reg", "tracking"):
             gk = torch.from_numpy(g[k]).to(DEV)
             print(k, "engine vs golden %.3e   eager vs golden %.3e" % (rel(eo[k], gk), rel(out[k], gk)))
-        print("feat engine vs golden %.3e" % rel(eng.feat, torch.from_numpy(g["feat"]).to(DEV)))
+        if "feat" in g:
+            print("feat engine vs golden %.3e" % rel(eng.feat, torch.from_numpy(g["feat"]).to(DEV)))
