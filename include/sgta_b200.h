@@ -240,6 +240,13 @@ int sgta_token_mlp(const void* att, const void* q, const void* fc_wt, const void
                    const void* ln3_w, const void* ln3_b, const void* wq_next, void* q_out, void* qp_out,
                    int T, int C, int hid, int dffn, float eps, void* stream);
 
+/* Token-row Linear layers of the fusion (dla.py:868-876 w_q / w_k / w_v of MHCA_ein; :1499-1502 cat_layer applied to
+ * cat([out, cur_query], -1) at :1006-1018):   y[m,n] = act( sum_k [x1 | x2][m,k] * w[n,k] + bias[n] )
+ * x1 [M,K1], x2 [M,K2] or NULL (K2 = 0), w [N,K1+K2] (nn.Linear weight as stored), bias [N] or NULL, y [M,N]; fp32,
+ * row-major; K1, K2 multiples of 16, N of 4; relu != 0 applies ReLU.  fp32 FMA, ascending k (replaces library SGEMMs). */
+int sgta_token_linear(const void* x1, int K1, const void* x2, int K2, const void* w, const void* bias,
+                      void* y, int M, int N, int relu, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Structure-prior maps: replaces the host rendering + 4 H2D copies per clip
  * and frame of lib/sgta_detector.py:528-540 (sgtapose/utilities.py:1045-1057 get_prev_hm_wo_noise,

@@ -39,7 +39,11 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // slots or loads (tools/dcn_bench.py), so they get 16 warps (2 rows per lane) where the plain gathers keep 8 (4 rows;
 // measured with 16: stem unchanged, level0 -5 %, level1 / stride-2 convs +6..+24 %: a net loss)
 template <int PROD> struct GProd { static constexpr int warps = PROD == 0 ? 16 : 8; };
-template <int PROD> struct GThreads { static constexpr int value = (GProd<PROD>::warps + 2 + 4) * 32; };   // + B loader, MMA, 4 epilogue warps
+// warps: [producers | 4 epilogue warps | B loader, MMA issuer, 2 idle] -- every role group is a whole warpgroup, so
+// fp32 mode can move registers between them with setmaxnreg (the band-drain epilogue keeps NT accumulators per thread)
+template <int PROD> struct GThreads { static constexpr int value = (GProd<PROD>::warps + 4 + 4) * 32; };
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
                                                          // each, tests/cuda/tma_bw_probe.cu): spread them over 4
 constexpr int S_EPI_NH = 2;                              // epilogue warps per TMEM lane quadrant (each takes half the columns)
@@ -74,7 +78,17 @@ struct ConvP {
   int b_resident;        // gather kernels: all weight blocks stay in shared memory (n_tiles == 1)
   int stg_bytes;         // EPI_PL: bytes of the epilogue's store staging tile (one 64-channel chunk x planes) at the head of smem
   int dbg;               // tools/conv_bench.py: 1 = skip A copies, 2 = skip B copies, 4 = skip epilogue math
+  // dcn_tile_kernel: output tiles of 8 x 16 pixels; the input tile + halo is staged in shared memory
+  int tile2d, tiles_x, tiles_y, halo, LW, LH, xt_plane;
 };
+
+// dcn_tile_kernel: output row (padded-frame index) of TMEM lane `row` of tile t
+__device__ __forceinline__ int tile_row_m(const ConvP& p, int t, int row) {
+  const int per = p.tiles_x * p.tiles_y;
+  const int b = t / per, r = t - b * per;
+  const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+  return (b * (p.Ho + 2) + ty * 8 + (row >> 4) + 1) * (p.Wo + 2) + tx * 16 + (row & 15) + 1;
+}
 
 static int g_dbg = 0;
 
@@ -411,7 +425,7 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
     rd.next();
     if (p.dbg & 4) continue;
     EpiRow e;
-    epi_row_setup(p, m0 + q * 32 + lane, e);
+    epi_row_setup(p, p.tile2d ? tile_row_m(p, t / p.n_tiles, q * 32 + lane) : m0 + q * 32 + lane, e);
     if (p.epi == SGTA_EPI_STEM) {
       // N = 32: out[c] = relu(bn_a(acc[c])) + relu(bn_b(acc[16+c])), c < 16   (dla.py:325-331); NH = 1 here
       if (NG >= 2 && e.valid) {
@@ -435,23 +449,23 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
       if ((g0 + g) * 16 < NT) epi_finish<2>(p, e, nt * NT + (g0 + g) * 16, acc[g]);
   }
 }
-template <int NH, bool BACKOFF>
+template <int NH, bool BACKOFF, int MAXNG = 8 / NH>
 __device__ __forceinline__ void fp32_epilogue(const ConvP& p, uint32_t tmem, int total, int nbands, int q, int half, int lane,
                                               uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty) {
-  const int per = ((p.NT + 15) / 16 + NH - 1) / NH;          // 16-column groups per thread
+  const int per = ((p.NT + 15) / 16 + NH - 1) / NH;          // 16-column groups per thread (the launcher keeps it <= MAXNG)
   if (per <= 1) fp32_epilogue_loop<1, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
   else if (per <= 2) fp32_epilogue_loop<2, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
-  else if (per <= 4 || NH > 1) fp32_epilogue_loop<4, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
-  else if constexpr (NH == 1) fp32_epilogue_loop<8, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
+  else if (per <= 4 || MAXNG <= 4) fp32_epilogue_loop<4, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
+  else if constexpr (MAXNG > 4) fp32_epilogue_loop<8, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
 }
 
 // NH epilogue warps per lane quadrant; `half` in [0, NH) is this warp's share
 template <int NS, int NH>
 __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row, uint32_t stage_s,
-                                              int half, uint64_t* release) {
+                                              int half, uint64_t* release, int m_abs = -1) {
   const int NT = p.NT;
   EpiRow e;
-  e.m = m0 + row;
+  e.m = m_abs >= 0 ? m_abs : m0 + row;
   decode_row(p, e.m, e.px, e.py, e.b);
   e.inP = e.m < p.P;
   e.valid = e.inP && e.px >= 1 && e.px <= p.Wo && e.py >= 1 && e.py <= p.Ho;
@@ -735,9 +749,14 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
 }
 
 // =============================================================================== gather kernel
-template <int PROD, int NS>
+// WIDE (fp32 mode only): N tiles of more than 64 columns -- the epilogue threads then hold up to 128 accumulators.
+// Register budget at launch: 768 x 80 (DCN) or 512 x 128 (plain gathers); the B loader / MMA warpgroup gives up all
+// but 40 per thread, which takes the DCN epilogue warpgroup to 120 (152 when the producers go down to 72 as well)
+// and the plain gathers' to 208.
+template <int PROD, int NS, int WIDE = 0>
 __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(const __grid_constant__ ConvP p) {
   constexpr int G_PROD_WARPS = GProd<PROD>::warps;
+  constexpr int W_EPI = G_PROD_WARPS, W_BLD = G_PROD_WARPS + 4, W_MMA = G_PROD_WARPS + 5;
   constexpr int RPL = TM / (G_PROD_WARPS * 4);          // rows per lane and K block: 4 (8 warps) or 2 (16 warps)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align1024(smem_raw);
@@ -763,7 +782,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
     for (int s = 0; s < 6; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4); }
     fence_mbar_init();
   }
-  if (warp == G_PROD_WARPS + 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  if (warp == W_MMA) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -774,6 +793,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
 
   if (warp < G_PROD_WARPS) {
     // ================================================================== A producers
+    if constexpr (NS == 2 && WIDE && PROD == PROD_DCN) reg_dec<72>();
     // lane = (sub, c8): 8 lanes cover one 128-byte row, a warp-wide load covers 4 whole rows
     const int sub = lane >> 3, c8 = lane & 7;
     const int iWp = p.in_Wp, iHp = p.in_Hp;
@@ -1018,7 +1038,9 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
         }
       }
     }
-  } else if (warp == G_PROD_WARPS) {
+  } else if (warp >= W_BLD) {
+   if constexpr (NS == 2) reg_dec<40>();
+   if (warp == W_BLD) {
     // ==================================================================== B loader
     if (lane == 0) {
       if (p.b_resident) {
@@ -1044,7 +1066,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
         }
       }
     }
-  } else if (warp == G_PROD_WARPS + 1) {
+   } else if (warp == W_MMA) {
     // ==================================================================== MMA issuer
     const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
     constexpr int R = AccR<NS>::value;
@@ -1106,12 +1128,16 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
         if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
       }
     }
+   }
   } else {
     // ==================================================================== epilogue warps
     const int q = warp & 3;
     if constexpr (NS == 2) {
+      if constexpr (PROD == PROD_DCN) { if constexpr (WIDE) reg_inc<152>(); else reg_inc<120>(); }
+      else reg_inc<208>();
       constexpr int BAND_KB = BAND_KSTEPS / 4;
-      fp32_epilogue<1, true>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane, slot_full, slot_empty, acc_empty);
+      fp32_epilogue<1, true, (WIDE || PROD != PROD_DCN) ? 8 : 4>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane,
+                                                                  slot_full, slot_empty, acc_empty);
     } else {
       uint32_t as = 0, accph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -1131,7 +1157,340 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == G_PROD_WARPS + 1) tmem_dealloc_dyn(tmem, p.tmem_cols);
+  if (warp == W_MMA) tmem_dealloc_dyn(tmem, p.tmem_cols);
+}
+
+// =============================================================================== DCN tile kernel
+// The DeformConv layers on maps of >= 8 x 16 pixels (13 of the 16 at 384 x 384: dla.py:545).  Same GEMM, same
+// B loader / MMA issuer / epilogue protocol as conv_gather_kernel<PROD_DCN>; what changes is where the producers
+// gather from.  An M tile is a block of 8 x 16 output pixels, and for every 64-channel chunk the input block
+// plus a halo of `halo` pixels ((8 + 2h) x (16 + 2h) rows of 128 B per plane) is staged in shared memory by bulk
+// copies (one per image row and plane, issued by the 16 producer warps' lane 0).  The 4 x NS corner loads of a
+// sample are LDS.128 from that tile: 128 B/clk instead of the ~64 B/clk an LDG.128 that touches four cache lines
+// gets from L1, a fixed 29-cycle latency, no tag look-ups, and the unified L1 no longer has to stay large -- the
+// x tile, the operand ring and the sampling table fill the 227 KB.  Samples whose corners leave the staged
+// window (|offset| >= halo - 1) take the global-memory path of the old kernel, row by row.
+constexpr int D_PROD_WARPS = 16;
+constexpr int D_THREADS = 24 * 32;      // warps 0-15 producers | 16-19 epilogue | 20 B loader, 21 MMA issuer, 22-23 idle
+
+// WIDE = 1: N tiles of 128 columns in fp32 mode -- the epilogue threads then hold 128 accumulators each and need
+// 152 registers.  setmaxnreg moves registers only inside the CTA's own allocation (768 x 80 at launch): the B
+// loader / MMA warpgroup gives up 40 per thread, which takes the epilogue warpgroup to 120 (enough for 64 columns);
+// for 128 columns the producers go down to 72 as well.
+template <int NS, int WIDE>
+__global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_constant__ ConvP p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align1024(smem_raw);
+  const int NT = p.NT;
+  constexpr uint32_t a_plane = TM * 128u, a_bytes = a_plane * NS;
+  const uint32_t b_plane = (uint32_t)NT * 128u, b_bytes = b_plane * NS;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t xt_plane = (uint32_t)p.xt_plane;
+  unsigned char* xt = smem;                                    // [plane][LH][LW][128 B], rows as they lie in HBM
+  unsigned char* ring = smem + (size_t)xt_plane * NS;          // SA stages of [A | B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.SA * stage_bytes);
+  uint64_t *full = bars, *empty = bars + 8, *acc_full = bars + 16, *acc_empty = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* xbar = bars + 21;
+  uint64_t *slot_full = bars + 22, *slot_empty = bars + 28;
+  unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 48);      // sampling table (9*128*32 B)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 8; ++s) { mbar_init(&full[s], D_PROD_WARPS + 1); mbar_init(&empty[s], 1); }
+    mbar_init(xbar, D_PROD_WARPS);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 6; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 21) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int total = p.tiles_x * p.tiles_y * p.x.B;             // n_tiles == 1
+  const int nkb = p.nkb;
+  const int Wp = p.Wo + 2, Hp = p.Ho + 2;
+  const int per_img = p.tiles_x * p.tiles_y;
+
+  if (warp < D_PROD_WARPS) {
+    // ================================================================== A producers
+    if (WIDE) reg_dec<72>();
+    const int sub = lane >> 3, c8 = lane & 7;
+    int pst = 0;
+    uint32_t pph = 1, xph = 0;
+    const size_t plane_bytes = ((size_t)p.x.nchunks * p.x.rows) << 7;
+    constexpr int RPL = TM / (D_PROD_WARPS * 4);               // 2 rows per lane and K block
+    uint32_t soff[RPL];
+    int rr[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      rr[i] = warp * (4 * RPL) + i * 4 + sub;
+      soff[i] = sw128_offset((uint32_t)rr[i], (uint32_t)c8);
+    }
+    const uint32_t gx = (uint32_t)c8 << 4;
+    const uint32_t tab_s = smem_u32(tab), xt_s = smem_u32(xt);
+    const int h = p.halo, LW = p.LW, LH = p.LH;
+    const uint32_t seg_bytes = (uint32_t)LW * 128u;
+    const int ncopies = LH * NS;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int b = t / per_img, r_ = t - b * per_img;
+      const int tyi = r_ / p.tiles_x, txi = r_ - tyi * p.tiles_x;
+      const int y0 = tyi * 8, x0 = txi * 16;                   // un-padded origin of the output block
+      // padded-frame row of local (0, 0) of the staged window, as a global row index of the view
+      const long long g00 = (long long)p.x.guard + ((long long)b * Hp + (y0 + 1 - h)) * Wp + (x0 + 1 - h);
+      for (int kc = 0; kc < p.KC; ++kc) {
+        // every producer is done with the previous chunk's x tile (and, at kc == 0, with the previous table)
+        asm volatile("bar.sync 1, %0;" ::"n"(D_PROD_WARPS * 32) : "memory");
+        if (lane == 0) {
+          int mine = 0;
+          for (int i = warp; i < ncopies; i += D_PROD_WARPS) ++mine;
+          if (mine) mbar_arrive_expect_tx(xbar, (uint32_t)mine * seg_bytes);
+          else mbar_arrive(xbar);
+          for (int i = warp; i < ncopies; i += D_PROD_WARPS) {
+            const int pl = i / LH, ly = i - pl * LH;
+            const unsigned char* src = p.x.base +
+                ((((size_t)pl * p.x.nchunks + p.x.chunk0 + kc) * p.x.rows + (size_t)(g00 + (long long)ly * Wp)) << 7);
+            bulk_g2s(xt + (size_t)pl * xt_plane + (size_t)ly * seg_bytes, src, seg_bytes, xbar);
+          }
+        }
+        if (kc == 0) {
+          // ---- sampling table of the tile: per (tap, row) the shared-memory addresses of the four corner rows
+          // (plane 0, 16-byte group 0, swizzle of the row's HBM position folded in) and mask * bilinear weights;
+          // bit 31 of .x flags a sample outside the staged window: .x then holds the global row of corner 0
+          uint4* tab_o = reinterpret_cast<uint4*>(tab);
+          float4* tab_w = reinterpret_cast<float4*>(tab + 9 * TM * 16);
+          for (int e = tid; e < 9 * TM; e += D_PROD_WARPS * 32) {
+            const int row = e & (TM - 1), tap = e >> 7;
+            const int py = y0 + (row >> 4) + 1, px = x0 + (row & 15) + 1;       // padded coordinates
+            const float* om = p.om + ((size_t)((long long)b * Hp + py) * Wp + px) * 32;
+            const float dy = __ldg(om + 2 * tap), dx = __ldg(om + 2 * tap + 1), ml = __ldg(om + 18 + tap);
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            float sy = (float)(py - 1 + ky) + dy;
+            float sx = (float)(px - 1 + kx) + dx;
+            const bool in = sy > 0.f && sy < (float)(p.Ho + 1) && sx > 0.f && sx < (float)(p.Wo + 1);
+            const float msk = in ? 1.f / (1.f + __expf(-ml)) : 0.f;
+            sy = in ? sy : (float)py;                          // weight 0: any row of the window will do
+            sx = in ? sx : (float)px;
+            const float yf = floorf(sy), xf = floorf(sx);
+            const float ly_ = sy - yf, lx_ = sx - xf, hy = 1.f - ly_, hx = 1.f - lx_;
+            const int Y0 = (int)yf, X0 = (int)xf;
+            const int wy = Y0 - (y0 + 1 - h), wx = X0 - (x0 + 1 - h);
+            const uint32_t gr0 = (uint32_t)((long long)p.x.guard + ((long long)b * Hp + Y0) * Wp + X0);
+            uint4 o;
+            if (wy >= 0 && wy <= LH - 2 && wx >= 0 && wx <= LW - 2) {
+              const uint32_t l0 = (uint32_t)(wy * LW + wx), l2 = l0 + (uint32_t)LW;
+              const uint32_t gr2 = gr0 + (uint32_t)Wp;
+              o = make_uint4(xt_s + (l0 << 7) + ((gr0 & 7u) << 4), xt_s + ((l0 + 1u) << 7) + (((gr0 + 1u) & 7u) << 4),
+                             xt_s + (l2 << 7) + ((gr2 & 7u) << 4), xt_s + ((l2 + 1u) << 7) + (((gr2 + 1u) & 7u) << 4));
+            } else {
+              o = make_uint4(0x80000000u | gr0, 0u, 0u, 0u);
+            }
+            tab_o[e] = o;
+            tab_w[e] = make_float4(msk * hy * hx, msk * hy * lx_, msk * ly_ * hx, msk * ly_ * lx_);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(D_PROD_WARPS * 32) : "memory");
+        mbar_wait(xbar, xph);
+        xph ^= 1u;
+        const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&empty[pst], pph);
+          const uint32_t sA_s = smem_u32(ring + (size_t)pst * stage_bytes);
+          if (!(p.dbg & 1)) {
+            uint4 v[RPL][4][NS];
+            float4 w[RPL];
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+              const uint4 o4 = lds128(tab_s + (uint32_t)(tap * TM + rr[i]) * 16u);
+              const uint4 w4 = lds128(tab_s + (uint32_t)(9 * TM + tap * TM + rr[i]) * 16u);
+              w[i] = make_float4(__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w));
+              if (o4.x & 0x80000000u) {
+                // outside the staged window: corner rows from global memory
+                const uint32_t r0 = o4.x & 0x7fffffffu;
+                const uint32_t rws[4] = {r0, r0 + 1u, r0 + (uint32_t)Wp, r0 + (uint32_t)Wp + 1u};
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) {
+                  const unsigned char* src = xk + ((size_t)rws[cn] << 7) + ((((rws[cn] & 7u) << 4)) ^ gx);
+                  v[i][cn][0] = __ldg(reinterpret_cast<const uint4*>(src));
+                  if (NS == 2) v[i][cn][NS - 1] = __ldg(reinterpret_cast<const uint4*>(src + plane_bytes));
+                }
+              } else {
+                const uint32_t off[4] = {o4.x ^ gx, o4.y ^ gx, o4.z ^ gx, o4.w ^ gx};
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) {
+                  v[i][cn][0] = lds128(off[cn]);
+                  if (NS == 2) v[i][cn][NS - 1] = lds128(off[cn] + xt_plane);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+              const float wc[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+              uint4 e0, e1 = make_uint4(0, 0, 0, 0);
+              if (NS == 2) {
+                // hi plane blended in fp32; lo plane (a 2^-11-scaled correction) in packed fp16 (2^-21 relative)
+                float H[8];
+                __half2 L[4];
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) {
+                  const uint32_t hv[4] = {v[i][cn][0].x, v[i][cn][0].y, v[i][cn][0].z, v[i][cn][0].w};
+                  const uint32_t lv[4] = {v[i][cn][NS - 1].x, v[i][cn][NS - 1].y, v[i][cn][NS - 1].z, v[i][cn][NS - 1].w};
+                  const __half2 wh = __float2half2_rn(wc[cn]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 hf = unpack_h2(hv[j]);
+                    const __half2 lh = *reinterpret_cast<const __half2*>(&lv[j]);
+                    if (cn == 0) {
+                      H[2 * j] = wc[0] * hf.x; H[2 * j + 1] = wc[0] * hf.y;
+                      L[j] = __hmul2(wh, lh);
+                    } else {
+                      H[2 * j] = fmaf(wc[cn], hf.x, H[2 * j]); H[2 * j + 1] = fmaf(wc[cn], hf.y, H[2 * j + 1]);
+                      L[j] = __hfma2(wh, lh, L[j]);
+                    }
+                  }
+                }
+                uint32_t eh[4], el[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 lf = __half22float2(L[j]);
+                  const float a = fmaf(lf.x, LO_INV, H[2 * j]), b2 = fmaf(lf.y, LO_INV, H[2 * j + 1]);
+                  const __half2 hh = __floats2half2_rn(a, b2);
+                  const float2 hb = __half22float2(hh);
+                  eh[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                  el[j] = pack_h2((a - hb.x) * LO_SCALE, (b2 - hb.y) * LO_SCALE);
+                }
+                e0 = make_uint4(eh[0], eh[1], eh[2], eh[3]);
+                e1 = make_uint4(el[0], el[1], el[2], el[3]);
+              } else {
+                // bf16 mode: the blend itself runs in packed bf16 (four HFMA2.BF16 per corner, no unpack / pack)
+                __nv_bfloat162 o2[4];
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) {
+                  const uint32_t bv[4] = {v[i][cn][0].x, v[i][cn][0].y, v[i][cn][0].z, v[i][cn][0].w};
+                  const __nv_bfloat162 wb = __float2bfloat162_rn(wc[cn]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&bv[j]);
+                    o2[j] = cn == 0 ? __hmul2(wb, xv) : __hfma2(wb, xv, o2[j]);
+                  }
+                }
+                e0 = make_uint4(*reinterpret_cast<uint32_t*>(&o2[0]), *reinterpret_cast<uint32_t*>(&o2[1]),
+                                *reinterpret_cast<uint32_t*>(&o2[2]), *reinterpret_cast<uint32_t*>(&o2[3]));
+              }
+              sts128(sA_s + soff[i], e0);
+              if (NS == 2) sts128(sA_s + a_plane + soff[i], e1);
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[pst]);
+          if (++pst == p.SA) { pst = 0; pph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp < D_PROD_WARPS + 4) {
+    // ==================================================================== epilogue warps
+    if (WIDE) reg_inc<152>();
+    else reg_inc<120>();
+    const int q = warp & 3;
+    if constexpr (NS == 2) {
+      constexpr int BAND_KB = BAND_KSTEPS / 4;
+      fp32_epilogue<1, true, WIDE ? 8 : 4>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane, slot_full, slot_empty, acc_empty);
+    } else {
+      uint32_t as = 0, accph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        mbar_wait_backoff(&acc_full[as], accph);
+        tc_fence_after();
+        if (!(p.dbg & 4))
+          epilogue_tile<NS, 1>(p, tmem + as * (uint32_t)NT + ((uint32_t)(q * 32) << 16), 0, 0, q * 32 + lane, 0u, 0, nullptr,
+                               tile_row_m(p, t, q * 32 + lane));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        as ^= 1u;
+        if (as == 0) accph ^= 1u;
+      }
+    }
+  } else {
+    reg_dec<40>();
+    if (warp == 20) {
+      // ==================================================================== B loader
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 1;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+          int kc = 0, tap = 0;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int blk = tap * p.KC + kc;                   // producers walk (kc outer, tap inner); packed blocks are (tap, kc)
+            mbar_wait(&empty[s], ph);
+            mbar_arrive_expect_tx(&full[s], b_bytes);
+            bulk_g2s(ring + (size_t)s * stage_bytes + a_bytes, p.wpack + (size_t)blk * b_bytes, b_bytes, &full[s]);
+            if (++s == p.SA) { s = 0; ph ^= 1u; }
+            if (++tap == 9) { tap = 0; ++kc; }
+          }
+        }
+      }
+    } else if (warp == 21) {
+      // ==================================================================== MMA issuer
+      const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+      constexpr int BAND_KB = BAND_KSTEPS / 4;
+      int s = 0;
+      uint32_t ph = 0, as = 0, accph = 1;
+      Ring rs{0u, 1u, p.nslots}, rd{0u, 1u, p.nd1};
+      const uint32_t smem0 = smem_u32(ring);
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        uint32_t tacc = 0, tD0 = 0, tD1 = 0, sl = 0;
+        if constexpr (NS == 2) {
+          mbar_wait(&acc_empty[rd.i], rd.ph);
+          tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+          rd.next();
+        } else {
+          mbar_wait(&acc_empty[as], accph);
+          tacc = tmem + as * (uint32_t)NT;
+        }
+        int kin = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[s], ph);
+          const uint32_t a0 = smem0 + (uint32_t)s * stage_bytes, b0 = a0 + a_bytes;
+          if constexpr (NS == 2) {
+            if (kin == 0) {
+              sl = rs.i;
+              mbar_wait(&slot_empty[sl], rs.ph);
+              tD0 = tmem + sl * (uint32_t)NT;
+              rs.next();
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              issue_kblock_f32(a0, a_plane, b0, b_plane, tD0, tD1, idesc, kin ? 1u : 0u, kb ? 1u : 0u);
+              mma_commit(&empty[s]);
+              if (kin + 1 == BAND_KB || kb == nkb - 1) mma_commit(&slot_full[sl]);
+            }
+            __syncwarp();
+            if (++kin == BAND_KB || kb == nkb - 1) kin = 0;
+          } else {
+            tc_fence_after();
+            if (elect_one()) {
+              if (kb == 0) issue_kblock<NS, true>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, 0);
+              else issue_kblock<NS, false>(a0, a_plane, b0, b_plane, tacc, (uint32_t)NT, idesc, 0);
+              mma_commit(&empty[s]);
+            }
+            __syncwarp();
+          }
+          if (++s == p.SA) { s = 0; ph ^= 1u; }
+        }
+        if constexpr (NS != 2) {
+          if (elect_one()) mma_commit(&acc_full[as]);
+          __syncwarp();
+          as ^= 1u;
+          if (as == 0) accph ^= 1u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 21) tmem_dealloc_dyn(tmem, p.tmem_cols);
 }
 
 // =============================================================================== weights
@@ -1246,9 +1605,46 @@ static int launch_gather(ConvP& p, cudaStream_t st) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
-  cudaFuncSetAttribute(conv_gather_kernel<PROD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  conv_gather_kernel<PROD, NS><<<grid, GThreads<PROD>::value, smem, st>>>(p);
+  if (NS == 2 && PROD == PROD_DCN && p.NT > 64) {
+    constexpr int W = (NS == 2 && PROD == PROD_DCN) ? 1 : 0;     // (only this combination instantiates the WIDE variant)
+    cudaFuncSetAttribute(conv_gather_kernel<PROD, NS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_gather_kernel<PROD, NS, W><<<grid, GThreads<PROD>::value, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(conv_gather_kernel<PROD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_gather_kernel<PROD, NS><<<grid, GThreads<PROD>::value, smem, st>>>(p);
+  }
   return check_launch("conv_gather_kernel");
+}
+
+// dcn_tile_kernel when the map tiles into 8 x 16 blocks, one N tile covers Cout and the staged window fits
+template <int NS>
+static int try_launch_dcn_tile(ConvP& p, cudaStream_t st) {
+  if ((p.dbg & 32) || p.Ho % 8 || p.Wo % 16 || p.n_tiles != 1) return -1;
+  const int a_bytes = TM * 128 * NS, b_bytes = p.NT * 128 * NS;
+  const int fixed = 1024 + 512 + 9 * TM * 32;
+  for (int SA = NS == 2 ? 2 : 3; SA >= 2; --SA) {
+    for (int h = 3; h >= 2; --h) {
+      const int LH = 8 + 2 * h, LW = 16 + 2 * h;
+      const int xt_plane = (LH * LW * 128 + 1023) & ~1023;
+      const int smem = xt_plane * NS + SA * (a_bytes + b_bytes) + fixed;
+      if (smem > SMEM_LIMIT) continue;
+      p.tile2d = 1; p.tiles_x = p.Wo / 16; p.tiles_y = p.Ho / 8; p.halo = h; p.LW = LW; p.LH = LH; p.xt_plane = xt_plane;
+      p.SA = SA; p.SB = 0; p.stg_bytes = 0; p.b_resident = 0;
+      static int sms = 0;
+      if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int total = p.tiles_x * p.tiles_y * p.x.B;
+      const int grid = total < sms ? total : sms;
+      if (NS == 2 && p.NT > 64) {
+        cudaFuncSetAttribute(dcn_tile_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        dcn_tile_kernel<NS, 1><<<grid, D_THREADS, smem, st>>>(p);
+      } else {
+        cudaFuncSetAttribute(dcn_tile_kernel<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        dcn_tile_kernel<NS, 0><<<grid, D_THREADS, smem, st>>>(p);
+      }
+      return check_launch("dcn_tile_kernel");
+    }
+  }
+  return -1;
 }
 
 static bool view_ok(const sgta_planes* v, int layout) {
@@ -1409,5 +1805,11 @@ extern "C" int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, co
   p.in_Wp = x->W + 2; p.in_Hp = x->H + 2;
   p.KC = Cin / 64; p.taps = 9; p.nkb = 9 * p.KC;
   cudaStream_t st = (cudaStream_t)stream;
+  // window-staged kernel where it measures faster: bf16 mode (1.72 vs 1.87 ms per step); in fp32 mode the blend is
+  // instruction-bound either way and the __ldg gather wins (3.55 vs 3.80 ms) -- debug flag 256 forces it, 32 disables it
+  rc = -1;
+  if (NS == 1 || (p.dbg & 256)) rc = NS == 2 ? try_launch_dcn_tile<2>(p, st) : try_launch_dcn_tile<1>(p, st);
+  if (rc >= 0) return rc;
+  p.tile2d = 0;
   return NS == 2 ? launch_gather<PROD_DCN, 2>(p, st) : launch_gather<PROD_DCN, 1>(p, st);
 }

@@ -104,21 +104,27 @@ def post_process_batch(scores, cts_wreg, trans_inv, out_thresh):
     return out
 
 
-def is_pnp(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K):
-    """geometric_vision.py:283-310: pose of the previous frame's detections, applied to the current
-    frame's keypoint positions and projected.  -> (prev_kp_projs, next_kp_projs_est)"""
-    ok, t, R = solve_pnp(prev_pos, prev_projs, camera_K)
+def is_pnp_pose(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K):
+    """`is_pnp` plus the pose it solved: -> (prev_kp_projs, next_kp_projs_est, pose [7] = t xyz + quaternion xyzw, or
+    None when PnP failed).  The pose of frame f-1's detections is what the sequence runner reports per frame."""
+    ok, t, q = solve_pnp_quat(prev_pos, prev_projs, camera_K)
     if not ok:
-        return prev_projs_all, prev_projs_all
+        return prev_projs_all, prev_projs_all, None
     T = np.eye(4)
-    T[:3, :3] = R
+    T[:3, :3] = rotation_from_quaternion(q)
     T[:3, -1] = t
     hom = np.hstack((next_pos, np.ones((next_pos.shape[0], 1))))
     aligned = np.transpose(np.matmul(T, np.transpose(hom)))[:, :3]
     est = np.transpose(np.matmul(camera_K, np.transpose(aligned)))
     est[:, 0] /= est[:, 2]
     est[:, 1] /= est[:, 2]
-    return prev_projs_all, est[:, :2]
+    return prev_projs_all, est[:, :2], np.concatenate([np.asarray(t, np.float64), np.asarray(q, np.float64)])
+
+
+def is_pnp(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K):
+    """geometric_vision.py:283-310: pose of the previous frame's detections, applied to the current
+    frame's keypoint positions and projected.  -> (prev_kp_projs, next_kp_projs_est)"""
+    return is_pnp_pose(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K)[:2]
 
 
 class LockstepDetector:
@@ -152,6 +158,7 @@ class LockstepDetector:
     def reset(self):
         self.frame = 0
         self.detected_kps = np.full((self.B, self.n_kp, 2), MISSING)
+        self.last_poses = np.full((self.B, 7), np.nan)       # PnP pose (t xyz, q xyzw) of the PREVIOUS frame's detections
         self.timing = {"host_pnp": 0.0, "host_post": 0.0, "steps": 0}
 
     # ------------------------------------------------------------------ host side of one clip
@@ -161,8 +168,23 @@ class LockstepDetector:
         kps = self.detected_kps[b]
         good = np.unique(np.where(kps > MISSING)[0])
         if len(good) == 0:
-            return None, None
-        return is_pnp(x3d_prev[good], kps[good], x3d_next, kps, self.K)
+            return None, None, None
+        return is_pnp_pose(x3d_prev[good], kps[good], x3d_next, kps, self.K)
+
+    def solve_poses(self, x3d):
+        """PnP pose [B,7] (t xyz + quaternion xyzw; NaN = nothing detected / solver failed) of the CURRENT
+        `detected_kps` against keypoint positions x3d [B,n_kp,3]: the per-frame pose the reference computes offline
+        from the saved detections (analysis.py:808-880 -> geometric_vision.solve_pnp).  During a sequence the same
+        solve happens inside `begin` of the next frame (`last_poses`); this is for the final frame."""
+        def one(b):
+            kps = self.detected_kps[b]
+            good = np.unique(np.where(kps > MISSING)[0])
+            if len(good) == 0:
+                return None
+            ok, t, q = solve_pnp_quat(x3d[b][good], kps[good], self.K)
+            return np.concatenate([t, q]) if ok else None
+        res = list(self.pool.map(one, range(self.B))) if self.pool else [one(b) for b in range(self.B)]
+        return np.stack([np.full(7, np.nan) if r is None else r for r in res])
 
     def _post(self, scores, cts_wreg):
         return post_process_batch(scores, cts_wreg, self.trans_inv, self.out_thresh)
@@ -211,6 +233,7 @@ class LockstepDetector:
             far = np.full((self.n_kp, 2), -1.0)                  # outside the raw image -> (0,0) -> nothing drawn
             prev = np.stack([far if r[0] is None else r[0] for r in res])
             nxt = np.stack([far if r[1] is None else r[1] for r in res])
+            self.last_poses = np.stack([np.full(7, np.nan) if r[2] is None else r[2] for r in res])
             for i, pts in enumerate((prev, nxt)):
                 self._c_in[i].copy_(torch.from_numpy(PR.affine_transform_and_clip(
                     pts, self.trans_input, self.S, self.S, self.raw_w, self.raw_h)))
@@ -272,7 +295,8 @@ class ClipGroups:
         """images_fn(f) -> frames of ALL clips for frame f ([B,...] uint8 raw or float32 network inputs);
         x3d_fn(f) -> [B,n_kp,3] keypoint positions w.r.t. the camera in frame f.
         before_begin(g, f, det): optional hook called right before group g's begin of frame f (tests and the
-        bench plant detections there).  Returns per-frame {'kps_raw' [B,n_kp,2], 'scores' [B,n_kp]}."""
+        bench plant detections there).  Returns per-frame {'kps_raw' [B,n_kp,2], 'scores' [B,n_kp], 'pose' [B,7] = PnP
+        pose (t xyz + quaternion xyzw) of that frame's detections against x3d_fn(f), NaN where there is none}."""
         G = len(self.dets)
         out = [dict() for _ in range(n_frames)]
         self.reset()                                   # a reused detector starts its clips again at frame 0
@@ -288,6 +312,13 @@ class ClipGroups:
         def finish(g, f):
             out[f][g] = self.dets[g].finish()
 
+        def pose_of(g, f, final):
+            """pose of frame f's detections: solved inside begin(g, f + 1), or explicitly after the last frame"""
+            d = self.dets[g]
+            if x3d_fn is None or not hasattr(d, "last_poses"):
+                return np.full((d.B, 7), np.nan)
+            return d.solve_poses(self._slice(x3d_fn(f), g)) if final else d.last_poses.copy()
+
         for g in range(G):
             begin(g, 0)
         for f in range(n_frames):
@@ -295,4 +326,7 @@ class ClipGroups:
                 finish(g, f)
                 if f + 1 < n_frames:
                     begin(g, f + 1)
-        return [{k: np.concatenate([fr[g][k] for g in range(G)]) for k in ("kps_raw", "scores")} for fr in out]
+                    out[f][g]["pose"] = pose_of(g, f, False)
+                else:
+                    out[f][g]["pose"] = pose_of(g, f, True)
+        return [{k: np.concatenate([fr[g][k] for g in range(G)]) for k in ("kps_raw", "scores", "pose")} for fr in out]

@@ -22,7 +22,6 @@ mode="fp32": fp32 activations, F32X3 split-bf16 MMAs (parity bound 1e-3 relative
 mode="bf16": bf16 activations and MMAs, fp32 accumulate (stated looser bound).
 """
 import torch
-import torch.nn.functional as F
 
 from . import decode, fusion
 from . import planes as P
@@ -254,12 +253,12 @@ class InferenceEngine:
             p = "transformer.%d.layers.0" % i
             a = p + ".cross_attn"
             heads = 8
-            Kp = F.linear(pre_key, sd[a + ".w_k.weight"])            # K, V are shared by the 3 layers
-            Vp = F.linear(pre_key, sd[a + ".w_v.weight"])
+            Kp = fusion.token_linear(pre_key, sd[a + ".w_k.weight"])   # K, V are shared by the 3 layers
+            Vp = fusion.token_linear(pre_key, sd[a + ".w_v.weight"])
             scale = (Kp.shape[-1] // heads) ** 0.5
             pos = sd[a + ".pos_embed"] if self.use_pos else None
             q = cur_q
-            qp = F.linear(q, sd[a + ".w_q.weight"])
+            qp = fusion.token_linear(q, sd[a + ".w_q.weight"])
             for layer in range(3):                                    # one shared layer (dla.py:788-789)
                 att = fusion.attention_core(qp, Kp, Vp, pos, heads, scale)
                 # fc + residual + LN1 + FFN + residual + LN3 (+ the next layer's w_q) in one launch
@@ -271,8 +270,8 @@ class InferenceEngine:
                                          sd[a + ".w_q.weight"] if layer < 2 else None)
             out = q
         c = "cat_layer.%d" % i
-        rows = F.linear(F.relu(F.linear(torch.cat([out, cur_q], -1), sd[c + ".0.weight"], sd[c + ".0.bias"])),
-                        sd[c + ".2.weight"], sd[c + ".2.bias"])
+        hid = fusion.token_linear(out, sd[c + ".0.weight"], sd[c + ".0.bias"], x2=cur_q, relu=True)   # cat folded in
+        rows = fusion.token_linear(hid, sd[c + ".2.weight"], sd[c + ".2.bias"])
         P.scatter_tokens(feats.full, B, cur_ids, rows, C)
         return feats.view(B, B)
 

@@ -172,6 +172,25 @@ class MHCA_ein(nn.Module):
         return self.fc(out)
 
 
+def token_linear(x, w, bias=None, x2=None, relu=False):
+    """nn.Linear on token rows in our own kernel: act([x | x2] w^T + bias).  x [..., K1] (and x2 [..., K2]) fp32 CUDA,
+    w [N, K1+K2] as nn.Linear stores it.  The K/V/first-Q projections (dla.py:868-876) and both layers of
+    cat_layer (dla.py:1499-1502; the torch.cat of :1015 is folded into the first one).  Inference only."""
+    x = x.contiguous()
+    K1 = x.shape[-1]
+    K2 = 0 if x2 is None else x2.shape[-1]
+    if x2 is not None:
+        x2 = x2.contiguous()
+    N = w.shape[0]
+    if w.shape[1] != K1 + K2:
+        raise _lib.SgtaError("token_linear: weight [%d,%d] does not match K = %d + %d" % (N, w.shape[1], K1, K2))
+    y = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=torch.float32)
+    M = x.numel() // K1
+    _lib.call("sgta_token_linear", _lib.ptr(x), K1, _lib.ptr(x2), K2, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), M, N,
+              int(bool(relu)), _lib.stream())
+    return y
+
+
 def token_mlp(att, q, fc_wt, fc_b, ln1_w, ln1_b, w1, b1, w2t, b2, ln3_w, ln3_b, wq_next=None, eps=1e-5):
     """Post-attention half of TransformerEncoderLayer.forward (dla.py:734-743) in ONE launch:
     q2 = LN3(q1 + FFN(q1)), q1 = LN1(fc(att) + q); also the next layer's query projection w_q q2 when

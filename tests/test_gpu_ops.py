@@ -174,6 +174,31 @@ def test_token_mlp_vs_torch(C, n, B):
     assert none is None and torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("M,K1,K2,N,relu,bias", [
+    (3 * 1183, 16, 0, 32, False, False),       # level-0 w_k / w_v / w_q (dla.py:868-876)
+    (2 * 343, 32, 32, 128, True, True),        # cat_layer.1[0] on cat([out, cur_query]) (dla.py:1499-1502)
+    (5 * 63, 256, 0, 64, False, True),         # cat_layer.2[2]
+    (7 * 32, 512, 512, 2048, True, True),      # cat_layer.5[0]: the 32 x 32 tile path
+    (7 * 32, 2048, 0, 512, False, True),       # cat_layer.5[2]
+    (37, 16, 16, 20, True, True),              # ragged M and N
+])
+def test_token_linear_vs_torch(M, K1, K2, N, relu, bias):
+    """Our Linear-on-token-rows kernel vs torch fp64 F.linear (+ cat, + ReLU)."""
+    import torch.nn.functional as F
+    from sgtapose_b200.fusion import token_linear
+    x1 = C_.gen(1, M, K1)
+    x2 = C_.gen(2, M, K2) if K2 else None
+    w = C_.gen(3, N, K1 + K2) * (1.0 / (K1 + K2)) ** 0.5
+    b = C_.gen(4, N) * 0.1 if bias else None
+    xin = torch.cat([x1, x2], -1) if K2 else x1
+    ref = F.linear(xin.double(), w.double(), b.double() if bias else None)
+    if relu:
+        ref = F.relu(ref)
+    out = token_linear(x1.to(DEV), w.to(DEV), b.to(DEV) if bias else None, x2=x2.to(DEV) if K2 else None, relu=relu)
+    assert out.shape == (M, N)
+    assert rel_err(out.cpu(), ref.float()) < 5e-6
+
+
 def test_attention_backward_vs_autograd():
     from sgtapose_b200.fusion import attention_core
     B, n, heads, d = 2, 63, 8, 16

@@ -185,16 +185,31 @@ DCN_CFGS = [  # B, Cin, Cout, H, W
     (1, 64, 128, 12, 20),
     (1, 256, 256, 12, 12),
     (1, 512, 256, 6, 6),
-    (3, 128, 128, 16, 16),
+    (3, 128, 128, 16, 16),      # 8 x 16 tiles: dcn_tile_kernel (window staged in shared memory), big offsets -> fallback rows
+    (2, 64, 64, 32, 32),        # dcn_tile_kernel, halo 3
+    (1, 128, 64, 48, 48),       # BASELINE #6/#8/#10/#12
+    (2, 64, 64, 96, 96),        # BASELINE #7/#9/#11/#13/#15
+    (1, 64, 128, 8, 48),
 ]
 
 
 @pytest.mark.parametrize("cfg", DCN_CFGS)
 @pytest.mark.parametrize("ns", [1, 2])
-def test_dcn_planes_vs_oracle(cfg, ns):
+@pytest.mark.parametrize("route", ["gather", "tile"])
+def test_dcn_planes_vs_oracle(cfg, ns, route):
     """DeformConv = offset/mask conv (shift-GEMM, fp32 rows out) + fused bilinear-gather DCN GEMM
-    with folded bias/BN + ReLU, vs the CPU oracle (torchvision deform_conv2d semantics)."""
-    from sgtapose_b200 import planes as P
+    with folded bias/BN + ReLU, vs the CPU oracle (torchvision deform_conv2d semantics).  Both producers are
+    covered in both modes: the __ldg gather kernel (debug flag 32 = never stage) and the window-staged tile kernel
+    (flag 256 = stage whenever the map tiles into 8 x 16 blocks; the default picks per mode)."""
+    from sgtapose_b200 import _lib, planes as P
+    old = _lib.load().sgta_debug_flags(32 if route == "gather" else 256)
+    try:
+        _dcn_planes_case(cfg, ns, P)
+    finally:
+        _lib.load().sgta_debug_flags(old)
+
+
+def _dcn_planes_case(cfg, ns, P):
     B, Ci, Co, H, W = cfg
     big = Ci == 128
     x = C.gen(21, B, Ci, H, W)
