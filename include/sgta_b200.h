@@ -102,6 +102,13 @@ typedef struct sgta_planes {
 #define SGTA_EPI_F32ROWS 2  /* y_f32[p*ld_f32 + o] for every padded row p (DCN offset/mask)    */
 #define SGTA_EPI_NCHW 3     /* y_f32 [B, n_valid, Ho, Wo] fp32 (heads; act may be sigmoid)     */
 #define SGTA_EPI_STEM 4     /* Cout == 32 -> SC view with 16 ch: relu(a[c]) + relu(a[16+c])    */
+/* super-pixel forms of the first two layers: a GEMM row is a SUPER-PIXEL = 4 consecutive pixels of an
+ * image row; a 16-channel map [B,H,W] is then a 64-channel PL view [B,H,W/4] (channel j*16 + c = pixel j, channel c) */
+#define SGTA_EPI_STEM_SP 5  /* Cout == 128 = 4 px x (16+16): the dual-stem epilogue per pixel -> 64-channel PL view      */
+#define SGTA_EPI_SP2SC 6    /* Cout == 64 = 4 px x 16 ch -> 16-channel SC view [B,H,4*W]: pixel j of row (y,X) -> (y,4X+j) */
+/* A 3x3 convolution with EPI_SP2SC and Cin == 64 is taken to be a 16 -> 16 convolution over super-pixels: its weight
+ * matrix MUST be the Toeplitz expansion planes.superpixel_weight(w, 4, 4, 1) -- the left / right neighbour taps are
+ * zero except for their last / first pixel, and the kernel does not issue those all-zero K steps. */
 
 /* performance experiments only (tools/conv_bench.py): bit 0 skip A copies, bit 1 skip B copies,
  * bit 2 skip the epilogue, bit 4 skip the MMAs in the planes convolutions (results are then garbage); returns the old value */
@@ -125,10 +132,10 @@ int sgta_planes_conv(const sgta_planes* x, const void* wpack, const void* scale,
 /* Convolution on an SC input (stems dla.py:241-270, level0/1 :302-312, level2 entry).  K block
  * kb (64 wide = 128 bytes per output pixel) is made of 8/seg_groups segments; segment j is a
  * run of seg_groups*16 contiguous bytes starting at input row
- *   anchor(b,oy,ox) + seg_off[kb*2 + j],  anchor = frame(b) + (oy*stride)*(W+2*border) + ox*stride
+ *   anchor(b,oy,ox) + seg_off[kb*2 + j],  anchor = frame(b) + (oy*stride)*(W+2*border) + ox*stride_x
  * (HOST table; the caller builds the matching weight matrix). */
 int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
-                        const sgta_planes* y, int Cout, int stride, int Ho, int Wo, int nkb,
+                        const sgta_planes* y, int Cout, int stride, int stride_x, int Ho, int Wo, int nkb,
                         int seg_groups, const int* seg_off, int act, int epi, void* stream);
 /* DeformConv main GEMM (dla.py:538-550): DCNv2 3x3/s1/p1/d1/dg1 + folded bias/BN (+ReLU).
  * offset_mask: fp32 [padded rows][32] raw conv_offset_mask output (SGTA_EPI_F32ROWS). */

@@ -70,6 +70,8 @@ struct ConvP {
   int acc_stages;        // TMEM accumulator stages (2 = epilogue overlaps the next tile)
   int nslots, nd1;       // fp32 mode: D0 band slots (2..6) and D1 buffers (1..2) in TMEM, NT columns each
   int stride;
+  int spk;               // shift kernel: super-pixel weights, zero K steps of the neighbour taps skipped (EPI_SP2SC)
+  int sx;                // gather kernels: column stride of the input anchor (== stride, except the super-pixel stem: 4)
   int in_Wp, in_Hp;      // input frame (gather kernels)
   int seg_groups;        // SMALLC: 16-byte groups per segment (8 or 4)
   int seg_off[16];       // SMALLC: input row offset of segment j of K block kb at [kb*2 + j]
@@ -122,7 +124,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 template <int NS> struct AccR { static constexpr int value = NS == 2 ? 3 : 1; };
 
 // rb = (index of this block's first K step) mod R
-template <int NS, bool FIRST, int R = AccR<NS>::value>
+// KMASK: bit k set = K step k is issued (super-pixel weights: the K steps of a neighbour tap that are zero by
+// construction are skipped; FIRST then requires bit 0, R == 1)
+template <int NS, bool FIRST, int R = AccR<NS>::value, int KMASK = 15>
 __device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
                                              uint32_t tacc, uint32_t NT, uint32_t idesc, int rb) {
   // everything but the 14-bit start-address field of a descriptor is constant: build the four
@@ -134,6 +138,7 @@ __device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, 
   const uint32_t tD1 = tacc + (uint32_t)R * NT;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    if (!((KMASK >> k) & 1)) continue;
     int r = 0;
     if (R > 1) { r = rb + k; r = r >= R ? r - R : r; r = r >= R ? r - R : r; }
     const uint32_t tD0 = tacc + (uint32_t)r * NT;
@@ -147,15 +152,27 @@ __device__ __forceinline__ void issue_kblock(uint32_t a_addr, uint32_t a_plane, 
 
 // one band of the shift kernel: TAPS K blocks that share an A band (descriptors one row apart),
 // each with its own B slot; slots are released as soon as their MMAs retire
-template <int NS, bool FIRST, int TAPS, int R>
+// SPK (3 taps, R == 1): super-pixel weights (planes.superpixel_weight, 4 pixels x 16 channels): the left neighbour
+// contributes only its last pixel (K step 3), the right one only its first (K step 0) -- 6 K steps per band, not 12.
+// The centre tap goes first so that the overwriting first MMA of a tile is a full one.
+template <int NS, bool FIRST, int TAPS, int R, int SPK = 0>
 __device__ __forceinline__ void issue_band(uint32_t a_base, uint32_t a_plane, const uint32_t (&b_addr)[3], uint32_t b_plane,
                                            uint32_t tacc, uint32_t NT, uint32_t idesc, int rb, uint64_t* const (&b_rel)[3],
                                            uint64_t* a_rel) {
+  if constexpr (SPK && TAPS == 3) {
+    issue_kblock<NS, FIRST, R, 15>(a_base + 128u, a_plane, b_addr[1], b_plane, tacc, NT, idesc, rb);
+    mma_commit(b_rel[1]);
+    issue_kblock<NS, false, R, 8>(a_base, a_plane, b_addr[0], b_plane, tacc, NT, idesc, rb);
+    mma_commit(b_rel[0]);
+    issue_kblock<NS, false, R, 1>(a_base + 256u, a_plane, b_addr[2], b_plane, tacc, NT, idesc, rb);
+    mma_commit(b_rel[2]);
+  } else {
 #pragma unroll
-  for (int dx = 0; dx < TAPS; ++dx) {
-    if (dx == 0) issue_kblock<NS, FIRST, R>(a_base, a_plane, b_addr[0], b_plane, tacc, NT, idesc, rb);
-    else issue_kblock<NS, false, R>(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tacc, NT, idesc, rb + dx);
-    mma_commit(b_rel[dx]);
+    for (int dx = 0; dx < TAPS; ++dx) {
+      if (dx == 0) issue_kblock<NS, FIRST, R>(a_base, a_plane, b_addr[0], b_plane, tacc, NT, idesc, rb);
+      else issue_kblock<NS, false, R>(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tacc, NT, idesc, rb + dx);
+      mma_commit(b_rel[dx]);
+    }
   }
   mma_commit(a_rel);
 }
@@ -168,26 +185,38 @@ __device__ __forceinline__ void issue_band(uint32_t a_base, uint32_t a_plane, co
 // (hi*lo + lo*hi, scaled 2^-11) runs over the whole tile: its truncation is 2^-11 times smaller.
 // TMEM columns: [D0 slot 0 | D0 slot 1 | D1 of even tiles | D1 of odd tiles], NT each.
 constexpr int BAND_KSTEPS = 12;
+template <int KMASK = 15>
 __device__ __forceinline__ void issue_kblock_f32(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
                                                  uint32_t tD0, uint32_t tD1, uint32_t idesc, uint32_t acc0, uint32_t acc1) {
   const uint64_t ah = smem_desc_sw128(a_addr), bh = smem_desc_sw128(b_addr);
   const uint64_t al = smem_desc_sw128(a_addr + a_plane), bl = smem_desc_sw128(b_addr + b_plane);
+  constexpr int K0 = (KMASK & 1) ? 0 : (KMASK & 2) ? 1 : (KMASK & 4) ? 2 : 3;       // first issued K step carries acc0 / acc1
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    mma_bf16_ss(tD0, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, k == 0 ? acc0 : 1u);
-    mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, k == 0 ? acc1 : 1u);
+    if (!((KMASK >> k) & 1)) continue;
+    mma_bf16_ss(tD0, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, k == K0 ? acc0 : 1u);
+    mma_bf16_ss(tD1, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, k == K0 ? acc1 : 1u);
     mma_bf16_ss(tD1, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
   }
 }
-template <int TAPS>
+template <int TAPS, int SPK = 0>
 __device__ __forceinline__ void issue_band_f32(uint32_t a_base, uint32_t a_plane, const uint32_t (&b_addr)[3], uint32_t b_plane,
                                                uint32_t tD0, uint32_t tD1, uint32_t idesc, uint32_t acc0, uint32_t acc1,
                                                uint64_t* const (&b_rel)[3], uint64_t* a_rel) {
+  if constexpr (SPK && TAPS == 3) {
+    issue_kblock_f32<15>(a_base + 128u, a_plane, b_addr[1], b_plane, tD0, tD1, idesc, acc0, acc1);     // centre tap first
+    mma_commit(b_rel[1]);
+    issue_kblock_f32<8>(a_base, a_plane, b_addr[0], b_plane, tD0, tD1, idesc, 1u, 1u);
+    mma_commit(b_rel[0]);
+    issue_kblock_f32<1>(a_base + 256u, a_plane, b_addr[2], b_plane, tD0, tD1, idesc, 1u, 1u);
+    mma_commit(b_rel[2]);
+  } else {
 #pragma unroll
-  for (int dx = 0; dx < TAPS; ++dx) {
-    issue_kblock_f32(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tD0, tD1, idesc, dx == 0 ? acc0 : 1u,
-                     dx == 0 ? acc1 : 1u);
-    mma_commit(b_rel[dx]);
+    for (int dx = 0; dx < TAPS; ++dx) {
+      issue_kblock_f32(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], b_plane, tD0, tD1, idesc, dx == 0 ? acc0 : 1u,
+                       dx == 0 ? acc1 : 1u);
+      mma_commit(b_rel[dx]);
+    }
   }
   mma_commit(a_rel);
 }
@@ -275,6 +304,24 @@ __device__ __forceinline__ void epi_read(const ConvP& p, uint32_t tacc, int c0, 
   }
 }
 
+// EPI_SP2SC: the GEMM rows are super-pixels (4 pixels x 16 channels) of an Ho x Wo frame; pixel j of row e lands in
+// the SC output frame of Ho x 4*Wo pixels
+__device__ __forceinline__ long long sp2sc_row(const ConvP& p, const EpiRow& e, int j) {
+  return ((long long)e.b * (p.Ho + 2) + e.py) * (4 * p.Wo + 2) + 4 * (e.px - 1) + 1 + j;
+}
+
+// dual-stem epilogue of one output pixel: out[c] = relu(bn_a(a[c])) + relu(bn_b(b[c])), c < 16 (dla.py:325-331)
+__device__ __forceinline__ void stem_pixel(const ConvP& p, const float (&fa)[16], const float (&fb)[16], float (&lo8)[8],
+                                           float (&hi8)[8]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float va = fmaf(fa[j], __ldg(p.scale + j), __ldg(p.shift + j));
+    const float vb = fmaf(fb[j], __ldg(p.scale + 16 + j), __ldg(p.shift + 16 + j));
+    const float o = fmaxf(va, 0.f) + fmaxf(vb, 0.f);
+    if (j < 8) lo8[j] = o; else hi8[j - 8] = o;
+  }
+}
+
 // scale / shift / residual / activation / store of 16 columns held in registers
 template <int NS>
 __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int n, float (&o)[16]) {
@@ -295,7 +342,7 @@ __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int 
     o[4 * j] = fmaf(o[4 * j], a.x, b4.x); o[4 * j + 1] = fmaf(o[4 * j + 1], a.y, b4.y);
     o[4 * j + 2] = fmaf(o[4 * j + 2], a.z, b4.z); o[4 * j + 3] = fmaf(o[4 * j + 3], a.w, b4.w);
   }
-  if (p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC) {
+  if (p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC || p.epi == SGTA_EPI_SP2SC) {
     if (!e.staged && !e.valid) return;
     if (e.has_res) {
 #pragma unroll
@@ -324,7 +371,8 @@ __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int 
         sts128(a, e0);
         if (NS == 2) sts128(a + 16384u, e1);
       } else if (p.epi == SGTA_EPI_PL) pl_store8<NS>(p.y, ch >> 6, e.m, (ch & 63) >> 3, f);
-      else sc_store8<NS>(p.y, e.m, ch, f);
+      else if (p.epi == SGTA_EPI_SC) sc_store8<NS>(p.y, e.m, ch, f);
+      else sc_store8<NS>(p.y, sp2sc_row(p, e, ch >> 4), ch & 15, f);
     }
   } else if (p.epi == SGTA_EPI_F32ROWS) {
     if (!e.inP) return;
@@ -366,7 +414,7 @@ __device__ __forceinline__ void epi_row_setup(const ConvP& p, int m, EpiRow& e) 
   decode_row(p, e.m, e.px, e.py, e.b);
   e.inP = e.m < p.P;
   e.valid = e.inP && e.px >= 1 && e.px <= p.Wo && e.py >= 1 && e.py <= p.Ho;
-  const bool pl_like = p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC;
+  const bool pl_like = p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC || p.epi == SGTA_EPI_SP2SC;
   e.has_res = pl_like && e.valid && p.res.base != nullptr;
   e.staged = false;
   e.srow = 0; e.sxor = 0;
@@ -426,21 +474,24 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
     if (p.dbg & 4) continue;
     EpiRow e;
     epi_row_setup(p, p.tile2d ? tile_row_m(p, t / p.n_tiles, q * 32 + lane) : m0 + q * 32 + lane, e);
-    if (p.epi == SGTA_EPI_STEM) {
-      // N = 32: out[c] = relu(bn_a(acc[c])) + relu(bn_b(acc[16+c])), c < 16   (dla.py:325-331); NH = 1 here
+    if (p.epi == SGTA_EPI_STEM || p.epi == SGTA_EPI_STEM_SP) {
+      // N = 32 per output pixel: [16 image-conv | 16 heat-map-conv] columns; NH = 1 here.  EPI_STEM: one pixel per row
+      // (N = 32) -> SC row; EPI_STEM_SP: the row is a super-pixel of 4 pixels (N = 128) -> 32-byte group j of the PL row
       if (NG >= 2 && e.valid) {
-        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float va = fmaf(acc[0][j], __ldg(p.scale + j), __ldg(p.shift + j));
-          const float vb = fmaf(acc[NG >= 2 ? 1 : 0][j], __ldg(p.scale + 16 + j), __ldg(p.shift + 16 + j));
-          o[j] = fmaxf(va, 0.f) + fmaxf(vb, 0.f);
+        for (int j = 0; j < NG / 2; ++j) {
+          if (j * 32 < NT) {
+            float lo8[8], hi8[8];
+            stem_pixel(p, acc[NG >= 2 ? 2 * j : 0], acc[NG >= 2 ? 2 * j + 1 : 0], lo8, hi8);
+            if (p.epi == SGTA_EPI_STEM) {
+              sc_store8<2>(p.y, e.m, 0, lo8);
+              sc_store8<2>(p.y, e.m, 8, hi8);
+            } else {
+              pl_store8<2>(p.y, 0, e.m, 2 * j, lo8);
+              pl_store8<2>(p.y, 0, e.m, 2 * j + 1, hi8);
+            }
+          }
         }
-        float lo8[8], hi8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { lo8[j] = o[j]; hi8[j] = o[8 + j]; }
-        sc_store8<2>(p.y, e.m, 0, lo8);
-        sc_store8<2>(p.y, e.m, 8, hi8);
       }
       continue;
     }
@@ -469,31 +520,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int
   decode_row(p, e.m, e.px, e.py, e.b);
   e.inP = e.m < p.P;
   e.valid = e.inP && e.px >= 1 && e.px <= p.Wo && e.py >= 1 && e.py <= p.Ho;
-  if (p.epi == SGTA_EPI_STEM) {
-    // N = 32: out[c] = relu(bn_a(acc[c])) + relu(bn_b(acc[16+c])), c < 16   (dla.py:325-331)
+  if (p.epi == SGTA_EPI_STEM || p.epi == SGTA_EPI_STEM_SP) {
+    // 32 columns per output pixel: [16 image-conv | 16 heat-map-conv]   (dla.py:325-331); see fp32_epilogue_loop
     if (half != 0) return;
     const int R = p.acc_r;
-    float fa[16], fb[16];
-    read_acc16<NS>(tacc, NT, R, 0, fa);
-    read_acc16<NS>(tacc, NT, R, 16, fb);
-    if (e.valid) {
-      float o[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float va = fa[j], vb = fb[j];
-        va = fmaf(va, __ldg(p.scale + j), __ldg(p.shift + j));
-        vb = fmaf(vb, __ldg(p.scale + 16 + j), __ldg(p.shift + 16 + j));
-        o[j] = fmaxf(va, 0.f) + fmaxf(vb, 0.f);
+    for (int j = 0; j * 32 < NT; ++j) {
+      float fa[16], fb[16];
+      __syncwarp();
+      read_acc16<NS>(tacc, NT, R, 32 * j, fa);
+      read_acc16<NS>(tacc, NT, R, 32 * j + 16, fb);
+      if (e.valid) {
+        float lo8[8], hi8[8];
+        stem_pixel(p, fa, fb, lo8, hi8);
+        if (p.epi == SGTA_EPI_STEM) {
+          sc_store8<NS>(p.y, e.m, 0, lo8);
+          sc_store8<NS>(p.y, e.m, 8, hi8);
+        } else {
+          pl_store8<NS>(p.y, 0, e.m, 2 * j, lo8);
+          pl_store8<NS>(p.y, 0, e.m, 2 * j + 1, hi8);
+        }
       }
-      float lo8[8], hi8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { lo8[j] = o[j]; hi8[j] = o[8 + j]; }
-      sc_store8<NS>(p.y, e.m, 0, lo8);
-      sc_store8<NS>(p.y, e.m, 8, hi8);
     }
     return;
   }
-  const bool pl_like = p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC;
+  const bool pl_like = p.epi == SGTA_EPI_PL || p.epi == SGTA_EPI_SC || p.epi == SGTA_EPI_SP2SC;
   e.has_res = pl_like && e.valid && p.res.base != nullptr;
   e.staged = stage_s != 0 && p.epi == SGTA_EPI_PL && m0 + TM <= p.P;
   e.srow = stage_s + (uint32_t)row * 128u;
@@ -553,7 +603,7 @@ __device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, int cols) {
 }
 
 // =============================================================================== shift kernel
-template <int NS, int R>
+template <int NS, int R, int SPK = 0>
 __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_constant__ ConvP p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align1024(smem_raw);
@@ -683,11 +733,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
             tc_fence_after();
             if (elect_one()) {
               const uint32_t acc0 = ks ? 1u : 0u, acc1 = first ? 0u : 1u;
-              if (ntap_b == 3) issue_band_f32<3>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
+              if (ntap_b == 3) issue_band_f32<3, SPK>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
               else issue_band_f32<1>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
             }
             __syncwarp();
-            ks += ntap_b * 4;
+            ks += SPK ? 6 : ntap_b * 4;
             const bool last = kc == p.KC - 1 && band == nb - 1;
             if (ks >= BAND_KSTEPS || last) {
               if (elect_one()) mma_commit(&slot_full[sl]);
@@ -698,8 +748,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
             tc_fence_after();
             if (elect_one()) {
               if (ntap_b == 3) {
-                if (first) issue_band<NS, true, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
-                else issue_band<NS, false, 3, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+                if (first) issue_band<NS, true, 3, R, SPK>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
+                else issue_band<NS, false, 3, R, SPK>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
               } else {
                 if (first) issue_band<NS, true, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, 0, b_rel, &a_empty[st]);
                 else issue_band<NS, false, 1, R>(a_base, a_plane, b_addr, b_plane, tacc, (uint32_t)NT, idesc, rb, b_rel, &a_empty[st]);
@@ -724,7 +774,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     if constexpr (NS == 2) {
       // fp32 mode: drain every finished band into registers, then D1, then math + stores (under the next tile's MMAs)
       const int steps = p.KC * nb;                              // issue_band calls per tile, ntap_b * 4 K steps each
-      const int per = BAND_KSTEPS / (ntap_b * 4);               // ... per D0 band: 1 (3x3) or 3 (1x1)
+      const int per = BAND_KSTEPS / (SPK ? 6 : ntap_b * 4);     // ... per D0 band: 1 (3x3), 3 (1x1) or 2 (super-pixel 3x3)
       fp32_epilogue<S_EPI_NH, false>(p, tmem, total, (steps + per - 1) / per, q, half, lane, slot_full, slot_empty, acc_empty);
     } else {
       uint32_t as = 0, accph = 0;
@@ -970,7 +1020,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
           decode_row(p, m0 + rr[i], px, py, b);
           b = min(b, p.x.B - 1);                          // border / tail rows: any in-bounds address
           const int oy = min(max(py - 1, 0), p.Ho - 1), ox = min(max(px - 1, 0), p.Wo - 1);
-          anchor[i] = p.x.guard + b * iHp * iWp + oy * p.stride * iWp + ox * p.stride;
+          anchor[i] = p.x.guard + b * iHp * iWp + oy * p.stride * iWp + ox * p.sx;
         }
       };
       auto load_block = [&](uint4 (&dst)[RPL][NS]) {
@@ -1577,8 +1627,13 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
-  cudaFuncSetAttribute(conv_shift_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  conv_shift_kernel<NS, 1><<<grid, S_THREADS, smem, st>>>(p);
+  if (p.spk) {
+    cudaFuncSetAttribute(conv_shift_kernel<NS, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_shift_kernel<NS, 1, 1><<<grid, S_THREADS, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(conv_shift_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_shift_kernel<NS, 1><<<grid, S_THREADS, smem, st>>>(p);
+  }
   return check_launch("conv_shift_kernel");
 }
 
@@ -1688,11 +1743,19 @@ static int fill_output(ConvP& p, const sgta_planes* y, void* y_f32, int64_t ld_f
   } else if (epi == SGTA_EPI_SC || epi == SGTA_EPI_STEM) {
     SGTA_REQUIRE(view_ok(y, SGTA_LAYOUT_SC) && y->nplanes == nplanes && y->border == 1, "%s: bad SC output view", who);
     SGTA_REQUIRE(epi == SGTA_EPI_STEM ? (Cout == 32 && y->nchunks == 16) : y->nchunks == Cout, "%s: SC output channel mismatch", who);
+  } else if (epi == SGTA_EPI_STEM_SP) {
+    SGTA_REQUIRE(view_ok(y, SGTA_LAYOUT_PL) && y->nplanes == nplanes && y->border == 1 && Cout == 128 && y->chunk0 < y->nchunks,
+                 "%s: the super-pixel stem writes a 64-channel PL view (Cout = 4 pixels x 32)", who);
+  } else if (epi == SGTA_EPI_SP2SC) {
+    SGTA_REQUIRE(view_ok(y, SGTA_LAYOUT_SC) && y->nplanes == nplanes && y->border == 1 && Cout == 64 && y->nchunks == 16,
+                 "%s: EPI_SP2SC writes 4 pixels x 16 channels per row into a 16-channel SC view", who);
+    SGTA_REQUIRE(y->B == B && y->H == Ho && y->W == 4 * Wo, "%s: output geometry mismatch", who);
+    p.y = make_view(y);
   } else {
     SGTA_REQUIRE(epi == SGTA_EPI_F32ROWS || epi == SGTA_EPI_NCHW, "%s: bad epilogue", who);
     SGTA_REQUIRE(y_f32 && (epi == SGTA_EPI_NCHW || ld_f32 >= Cout), "%s: bad fp32 output", who);
   }
-  if (epi == SGTA_EPI_PL || epi == SGTA_EPI_SC || epi == SGTA_EPI_STEM) {
+  if (epi == SGTA_EPI_PL || epi == SGTA_EPI_SC || epi == SGTA_EPI_STEM || epi == SGTA_EPI_STEM_SP) {
     SGTA_REQUIRE(y->B == B && y->H == Ho && y->W == Wo, "%s: output geometry mismatch", who);
     p.y = make_view(y);
   }
@@ -1714,7 +1777,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
   p.dbg = g_dbg;
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
-  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
+  p.act = act; p.stride = stride; p.sx = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
   const int pad = ksize / 2;
   const int Ho = (x->H + 2 * pad - ksize) / stride + 1, Wo = (x->W + 2 * pad - ksize) / stride + 1;
   SGTA_REQUIRE(Ho > 0 && Wo > 0, "sgta_planes_conv: empty output");
@@ -1738,6 +1801,9 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
     if (stride == 1) {
       SGTA_REQUIRE(ksize == 1 || ksize == 3, "sgta_planes_conv: PL stride-1 kernels are 1x1 or 3x3");
       p.taps = ksize * ksize; p.nkb = p.taps * p.KC; p.a_rows = ksize == 3 ? 144 : 136;
+      // EPI_SP2SC = level0 over super-pixels: the weights come from planes.superpixel_weight (gin = gout = 4, 16
+      // channels), whose neighbour taps are zero outside one pixel -- those K steps are not issued
+      p.spk = epi == SGTA_EPI_SP2SC && ksize == 3 && Cin == 64 && !(p.dbg & 512);
       if (NS == 2 && NT == 128 && p.nkb <= 9) plan_acc(p, NS, true);
       const int Wp = x->W + 2;
       SGTA_REQUIRE(x->guard >= Wp + 1 + 8 && x->rows >= (int64_t)x->guard + (int64_t)p.m_tiles * TM + Wp + 16 + 8,
@@ -1754,7 +1820,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
 }
 
 extern "C" int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
-                                   const sgta_planes* y, int Cout, int stride, int Ho, int Wo, int nkb,
+                                   const sgta_planes* y, int Cout, int stride, int stride_x, int Ho, int Wo, int nkb,
                                    int seg_groups, const int* seg_off /*HOST [nkb*2]*/, int act, int epi, void* stream) {
   SGTA_REQUIRE(x && wpack && scale && shift && y && seg_off, "sgta_planes_conv_sc: null pointer");
   SGTA_REQUIRE(view_ok(x, SGTA_LAYOUT_SC), "sgta_planes_conv_sc: bad SC input view");
@@ -1767,7 +1833,8 @@ extern "C" int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, cons
   p.dbg = g_dbg;
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
-  p.act = act; p.stride = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
+  SGTA_REQUIRE(stride >= 1 && stride_x >= 1, "sgta_planes_conv_sc: strides must be positive");
+  p.act = act; p.stride = stride; p.sx = stride_x; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
   const long long P = (long long)x->B * (Ho + 2) * (Wo + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv_sc: too many pixels");
   p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.m_tiles = cdiv(P, TM);

@@ -42,7 +42,7 @@ def _fold_bn(sd, p, bias=None):
 
 class InferenceEngine:
     def __init__(self, state_dict, opt, batch, size=384, mode="fp32", device="cuda", fuse_sigmoid=False,
-                 skip_dead_levels=False, use_graph=True, superpixel_level0=False):
+                 skip_dead_levels=False, use_graph=True, superpixel=True):
         if mode not in ("fp32", "bf16"):
             raise ValueError("mode must be 'fp32' or 'bf16'")
         if size % 32:
@@ -53,10 +53,11 @@ class InferenceEngine:
         self.opt = opt
         self.fuse_sigmoid = fuse_sigmoid
         self.skip_dead_levels = skip_dead_levels
-        # EXPERIMENTAL, off by default, not yet validated on a GPU: run base.level0 as a 64 -> 64 PL
-        # convolution over super-pixels (4 px x 16 ch) on conv_shift_kernel, with a layout copy on either side.
-        # tools/superpixel_level0_check.py compares it with the default path.
-        self.superpixel_level0 = bool(superpixel_level0)
+        # super-pixel form of the two full-resolution layers: the dual stem as a gather-GEMM over groups of
+        # 4 output pixels (N = 128, a quarter of the rows) writing a 64-"channel" PL view [B,S,S/4], and base.level0 as
+        # a plain 64 -> 64 shift-GEMM over that view (A tiles by TMA) whose epilogue writes the 16-channel SC map the
+        # rest of the network reads.  superpixel=False keeps the per-pixel SC kernels (cross-check in the tests).
+        self.superpixel = bool(superpixel) and size % 4 == 0
         self.K_list = [int(getattr(opt, "k_list_%d" % (i + 1))) for i in range(6)]
         self.kernel_list = [int(getattr(opt, "ks%d" % (i + 1))) for i in range(6)]
         self.use_pos = bool(getattr(opt, "pos_embed", True))
@@ -104,7 +105,8 @@ class InferenceEngine:
         s["stem"] = P.ScConvSpec([(wi, 0), (wh, 3)], torch.cat([sa, sb]), torch.cat([ta, tb]), 4, 7, 1, 3, 3, S,
                                  self.ns)
         s["level0"] = self._sc_conv_bn("base.level0.0", "base.level0.1", 1, S, P.ACT_RELU)
-        if self.superpixel_level0:
+        if self.superpixel:
+            s["stem_sp"] = P.StemSuperSpec(wi, wh, torch.cat([sa, sb]), torch.cat([ta, tb]), S, self.ns)
             w0 = sd["base.level0.0.weight"].float()
             sc0, sh0 = _fold_bn(sd, "base.level0.1")
             s["level0_sp"] = P.ConvSpec(P.weight_matrix(P.superpixel_weight(w0, 4, 4, 1)), sc0.repeat(4), sh0.repeat(4),
@@ -154,11 +156,11 @@ class InferenceEngine:
         h1, h2, h3, h4, h5 = S // 2, S // 4, S // 8, S // 16, S // 32
         b = {}
         b["in4"] = pb(B2, 4, S, border=3)
-        b["f0"] = pb(B2, 16, S)
+        if self.superpixel:
+            b["f0sp"] = P.PlaneBuf(B2, 64, S, S // 4, ns, dev)           # stem output as super-pixels (4 px x 16 ch)
+        else:
+            b["f0"] = pb(B2, 16, S)
         b["l0"] = pb(B2, 16, S)
-        if self.superpixel_level0:
-            b["sp_in"] = P.PlaneBuf(B2, 64, S, S // 4, ns, dev)
-            b["sp_out"] = P.PlaneBuf(B2, 64, S, S // 4, ns, dev)
         b["l1"] = pb(B2, 32, h1)
         b["bot2"] = pb(B2, 32, h2)
         b["res2"] = pb(B2, 64, h2)
@@ -281,12 +283,11 @@ class InferenceEngine:
         i = self.inp
         P.pack_stem(i["pre_img"], i["pre_hm"], b["in4"].full, 0)
         P.pack_stem(i["x"], i["repro_hm"], b["in4"].full, B)
-        P.conv_sc(s["stem"], b["in4"].full, b["f0"].full, P.EPI_STEM)
-        if self.superpixel_level0:
-            P.superpixels(b["f0"].full, b["sp_in"].full, True)
-            P.conv(s["level0_sp"], b["sp_in"].full, b["sp_out"].full)
-            P.superpixels(b["l0"].full, b["sp_out"].full, False)
+        if self.superpixel:
+            P.conv_stem_sp(s["stem_sp"], b["in4"].full, b["f0sp"].full)
+            P.conv(s["level0_sp"], b["f0sp"].full, b["l0"].full, epi=P.EPI_SP2SC)
         else:
+            P.conv_sc(s["stem"], b["in4"].full, b["f0"].full, P.EPI_STEM)
             P.conv_sc(s["level0"], b["f0"].full, b["l0"].full, P.EPI_SC)
         P.conv_sc(s["level1"], b["l0"].full, b["l1"].full, P.EPI_SC)
         # level 2: Tree(1, 32->64, stride 2)

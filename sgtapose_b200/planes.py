@@ -15,7 +15,7 @@ import torch
 from . import _lib
 
 PL, SC = 0, 1
-EPI_PL, EPI_SC, EPI_F32ROWS, EPI_NCHW, EPI_STEM = 0, 1, 2, 3, 4
+EPI_PL, EPI_SC, EPI_F32ROWS, EPI_NCHW, EPI_STEM, EPI_STEM_SP, EPI_SP2SC = 0, 1, 2, 3, 4, 5, 6
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 
 
@@ -243,8 +243,62 @@ def conv_sc(spec, x, y, epi, act=None):
     Ho = (x.H + 2 * spec.pad - spec.ksize) // spec.stride + 1
     Wo = (x.W + 2 * spec.pad - spec.ksize) // spec.stride + 1
     _lib.call("sgta_planes_conv_sc", x.ref, _lib.ptr(spec.wpack), _lib.ptr(spec.scale), _lib.ptr(spec.shift), y.ref,
-              spec.Cout, spec.stride, Ho, Wo, spec.nkb, spec.seg_groups, spec.seg_off,
+              spec.Cout, spec.stride, spec.stride, Ho, Wo, spec.nkb, spec.seg_groups, spec.seg_off,
               spec.act if act is None else act, epi, _lib.stream())
+
+
+SP_G = 4        # pixels per super-pixel
+
+
+def stem_superpixel_matrix(wi, wh):
+    """Weight matrix [128, 7*64] of the dual 7x7 stem (dla.py:241-270, :325-331) over SUPER-PIXELS of 4 output pixels:
+    column block j*32 = output pixel j of the group ([16 image-conv | 16 heat-map-conv] channels); K block ky = kernel
+    row ky = the 16 input pixels x 4 channels [img(3) | hm(1)] starting at the group's first padded column, in the
+    8-byte-pixel order of the SC gather (K index = (i % 8)*8 + (i // 8)*4 + ch for input pixel i).  Output pixel j
+    reads input pixel i with kernel column kx = i - j (Toeplitz expansion; 10 of the 16 pixels carry weights)."""
+    wm = wi.new_zeros(SP_G * 32, 7 * 64)
+    for j in range(SP_G):
+        for w, cin_off, n_off in ((wi, 0, 0), (wh, 3, 16)):
+            co, ci = w.shape[:2]
+            for ky in range(7):
+                for i in range(16):
+                    kx = i - j
+                    if 0 <= kx < 7:
+                        kbase = ky * 64 + (i % 8) * 8 + (i // 8) * 4 + cin_off
+                        wm[j * 32 + n_off:j * 32 + n_off + co, kbase:kbase + ci] = w[:, :, ky, kx].float()
+    return wm
+
+
+class StemSuperSpec:
+    """The dual stem as ONE gather-GEMM over super-pixels: M = pixels / 4, N = 128, K = 7 blocks of 64 -- the same
+    FLOPs as the per-pixel form (N = 32) but a quarter of the rows, so a quarter of the producers' LDG -> STS traffic
+    and MMAs that are 4x wider per A byte.  Epilogue EPI_STEM_SP writes the 64-channel PL super-pixel view that the
+    level0 super-pixel convolution (`superpixel_weight`) reads by TMA."""
+
+    def __init__(self, wi, wh, scale, shift, in_W, nplanes):
+        dev = wi.device
+        Wp = in_W + 6                                   # the stem input frame has a 3-pixel border (= the padding)
+        seg_off = []
+        for ky in range(7):
+            seg_off += [ky * Wp, ky * Wp + 8]           # two 8-pixel (64-byte) segments of kernel row ky
+        self.seg_off = (ctypes.c_int * 14)(*seg_off)
+        self.nkb, self.seg_groups = 7, 4
+        wm = stem_superpixel_matrix(wi.float(), wh.float()).to(dev)
+        self.scale = scale.float().contiguous()
+        self.shift = shift.float().contiguous()
+        nbytes = _lib.load().sgta_planes_wpack_bytes(128, 7 * 64, nplanes)
+        self.wpack = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        _lib.call("sgta_planes_pack_weight", _lib.ptr(wm.contiguous()), _lib.ptr(self.wpack), 128, 7 * 64, nplanes, _lib.stream())
+        self.Cout = 128
+
+
+def conv_stem_sp(spec, x, y):
+    """x: SC view, 4 channels, border 3, [B,H,W];  y: PL view, 64 channels, [B,H,W/4]."""
+    if x.W % SP_G:
+        raise _lib.SgtaError("super-pixel stem: W must be a multiple of 4")
+    _lib.call("sgta_planes_conv_sc", x.ref, _lib.ptr(spec.wpack), _lib.ptr(spec.scale), _lib.ptr(spec.shift), y.ref,
+              spec.Cout, 1, SP_G, x.H, x.W // SP_G, spec.nkb, spec.seg_groups, spec.seg_off, ACT_NONE, EPI_STEM_SP,
+              _lib.stream())
 
 
 def dcn(x, om, wspec, scale, shift, y, relu=True):

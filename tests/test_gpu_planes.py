@@ -179,6 +179,49 @@ def test_conv_small_channel_layers(ns):
     assert rel_err(y3.to_nchw().cpu(), ref4) < TOL[ns] * 3
 
 
+@pytest.mark.parametrize("ns", [1, 2])
+@pytest.mark.parametrize("hw", [(40, 40), (22, 52)])
+def test_superpixel_stem_and_level0(ns, hw):
+    """Super-pixel forms of the two full-resolution layers (engine default): the dual 7x7 stem as a gather-GEMM over
+    groups of 4 output pixels (N = 128, EPI_STEM_SP -> 64-channel PL view [B,H,W/4]) and level0 as a 64 -> 64
+    shift-GEMM over that view with Toeplitz-expanded weights (EPI_SP2SC -> the 16-channel SC map), vs fp64 torch and
+    vs the per-pixel SC kernels (dla.py:241-270, :302-312, :325-331)."""
+    from sgtapose_b200 import planes as P
+    B, (H, W) = 3, hw
+    img, hm = C.gen(61, B, 3, H, W), C.gen(62, B, 1, H, W).abs()
+    wi, wh = C.gen(63, 16, 3, 7, 7) * 0.1, C.gen(64, 16, 1, 7, 7) * 0.2
+    sc, sh = C.gen(65, 32).abs() + 0.5, C.gen(66, 32) * 0.3
+    d = lambda t: t.double()
+    in4 = P.PlaneBuf(B, 4, H, W, ns, DEV, border=3)
+    P.pack_stem(img.to(DEV), hm.to(DEV), in4.full, 0)
+    q = torch.cat([img, hm], 1)                                 # the (bf16-)quantised input the kernels see
+    if ns == 1:
+        q = q.bfloat16().float()
+    ref0 = torch.relu(F.conv2d(d(q[:, :3]), d(wi), None, 1, 3) * d(sc)[None, :16, None, None] + d(sh)[None, :16, None, None]) + \
+        torch.relu(F.conv2d(d(q[:, 3:]), d(wh), None, 1, 3) * d(sc)[None, 16:, None, None] + d(sh)[None, 16:, None, None])
+    spec = P.StemSuperSpec(wi.to(DEV), wh.to(DEV), sc.to(DEV), sh.to(DEV), W, ns)
+    f0sp = P.PlaneBuf(B, 64, H, W // 4, ns, DEV)
+    P.conv_stem_sp(spec, in4.full, f0sp.full)
+    got0 = P.from_superpixels(f0sp.to_nchw(), 4).cpu()
+    assert rel_err(got0, ref0) < TOL[ns] * 3
+    # the per-pixel stem agrees too (same arithmetic, different tiling)
+    stem = P.ScConvSpec([(wi.to(DEV), 0), (wh.to(DEV), 3)], sc.to(DEV), sh.to(DEV), 4, 7, 1, 3, 3, W, ns)
+    f0 = P.PlaneBuf(B, 16, H, W, ns, DEV)
+    P.conv_sc(stem, in4.full, f0.full, P.EPI_STEM)
+    assert rel_err(f0.to_nchw().cpu(), got0) < TOL[ns] * 3
+    # level0 over super-pixels -> SC map
+    w0 = C.gen(67, 16, 16, 3, 3) * 0.1
+    s0, t0 = C.gen(68, 16).abs() + 0.5, C.gen(69, 16) * 0.1
+    ref1 = torch.relu(F.conv2d(d(got0), d(w0), None, 1, 1) * d(s0)[None, :, None, None] + d(t0)[None, :, None, None])
+    l0spec = P.ConvSpec(P.weight_matrix(P.superpixel_weight(w0.to(DEV), 4, 4, 1)), s0.to(DEV).repeat(4), t0.to(DEV).repeat(4),
+                        64, 3, 1, ns, P.ACT_RELU)
+    l0 = P.PlaneBuf(B, 16, H, W, ns, DEV)
+    P.conv(l0spec, f0sp.full, y=l0.full, epi=P.EPI_SP2SC)
+    got1 = l0.to_nchw().cpu()
+    assert rel_err(got1, ref1) < TOL[ns] * 3
+    assert float(l0.t.view(torch.int16).abs().sum()) > 0
+
+
 DCN_CFGS = [  # B, Cin, Cout, H, W
     (2, 64, 64, 24, 24),
     (1, 128, 64, 17, 13),

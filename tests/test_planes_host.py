@@ -55,3 +55,30 @@ def test_load_model_save_model_reference_call_forms(tmp_path):
     assert torch.equal(small.hm.weight, keep) and torch.equal(small.body.weight, src.body.weight)
     networks.load_model(small, path, types.SimpleNamespace(reset_hm=False, reuse_hm=True))
     assert torch.equal(small.hm.weight, src.hm.weight[:3])
+
+
+def test_stem_superpixel_matrix_vs_conv2d():
+    """Host half of the super-pixel stem (planes.stem_superpixel_matrix): the Toeplitz-expanded [128, 7*64] matrix,
+    applied to K blocks gathered exactly like the SC gather kernel does (kernel row ky = 16 padded input pixels x 4
+    channels from the group's first column, 8-byte-pixel order), equals the two 7x7 convolutions of dla.py:241-270."""
+    import torch
+    import torch.nn.functional as F
+    from sgtapose_b200 import planes as P
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 6, 12
+    img, hm = torch.randn(B, 3, H, W, generator=g, dtype=torch.float64), torch.randn(B, 1, H, W, generator=g, dtype=torch.float64)
+    wi, wh = torch.randn(16, 3, 7, 7, generator=g, dtype=torch.float64), torch.randn(16, 1, 7, 7, generator=g, dtype=torch.float64)
+    wm = P.stem_superpixel_matrix(wi, wh)
+    assert wm.shape == (128, 448)
+    x = F.pad(torch.cat([img, hm], 1), (3, 3 + 16, 3, 3))            # border 3 (+ slack on the right for the 16-pixel runs)
+    ref = torch.cat([F.conv2d(img, wi, None, 1, 3), F.conv2d(hm, wh, None, 1, 3)], 1)      # [B,32,H,W]
+    for b in range(B):
+        for y in range(H):
+            for X in range(W // 4):
+                a = torch.zeros(448, dtype=torch.float64)
+                for ky in range(7):
+                    for i in range(16):
+                        a[ky * 64 + (i % 8) * 8 + (i // 8) * 4:ky * 64 + (i % 8) * 8 + (i // 8) * 4 + 4] = x[b, :, y + ky, 4 * X + i]
+                out = wm @ a
+                for j in range(4):
+                    assert torch.allclose(out[32 * j:32 * j + 32], ref[b, :, y, 4 * X + j], atol=1e-5)     # the matrix is built in fp32
