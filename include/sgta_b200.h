@@ -220,6 +220,10 @@ int sgta_decode_peaks(const void* hm, const void* reg, const void* tracking, voi
 int sgta_decode_peaks_exact64(const void* hm, const void* reg, const void* tracking, void* scores,
                               void* inds, void* xs, void* ys, void* cts_wreg, void* trk,
                               const double* gauss_w, int B, int C, int h, int w, void* stream);
+/* Test hook: on != 0 makes sgta_decode_peaks blur every pixel of every map instead of the active box only (the box =
+ * rows / columns whose blurred row / column maxima can reach the 0.01 threshold; outputs are identical either way);
+ * returns the previous setting. */
+int sgta_decode_full_map(int on);
 /* Test hook: number of pixels sgta_decode_peaks re-evaluated in float64 since the last reset
  * (synchronises the device; count is a HOST pointer). */
 int sgta_decode_recheck_count(unsigned long long* count, int reset);

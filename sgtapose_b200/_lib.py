@@ -60,6 +60,7 @@ SIGNATURES = {
     "sgta_decode_peaks": (_I, [_P] * 9 + [_c.POINTER(_c.c_double)] + [_I] * 4 + [_P]),
     "sgta_decode_peaks_exact64": (_I, [_P] * 9 + [_c.POINTER(_c.c_double)] + [_I] * 4 + [_P]),
     "sgta_decode_recheck_count": (_I, [_c.POINTER(_c.c_uint64), _I]),
+    "sgta_decode_full_map": (_I, [_I]),
     "sgta_decode_nms_topk": (_I, [_P] * 5 + [_I] * 5 + [_P]),
     "sgta_nms3x3": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "sgta_soft_argmax": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),

@@ -140,7 +140,9 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
   float* Ks = att_smem;
   float* Vs = Ks + (size_t)nk * S;
   float* Part = Vs + (size_t)nk * S;         // [KS][ATT_ROWS][D + 2] partial (acc, m, l) per key split
-  float* Ps = Part + KS * ATT_ROWS * (D + 2);   // [ATT_ROWS][nk_pad]
+  float* Qs = Part + KS * ATT_ROWS * (D + 2);   // [ATT_ROWS][D] query rows of the current sample (prefetched like K / V:
+                                                // read straight from global they cost one exposed miss per sample and warp)
+  float* Ps = Qs + ATT_ROWS * D;                // [ATT_ROWS][nk_pad]
   const int h = blockIdx.y;
   const int HD = heads * D;
   const int row0 = blockIdx.x * ATT_ROWS;
@@ -157,10 +159,14 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
       for (int j = lane; j < nk; j += 32) Ps[r * nk_pad + j] = __ldg(prow + j) * LOG2E;
     }
   }
-  float4 kreg[PF], vreg[PF];
+  float4 kreg[PF], vreg[PF], qreg = make_float4(0.f, 0.f, 0.f, 0.f);
   auto prefetch = [&](int b) {
     const float* kb = k + (long long)b * nk * HD + h * D;
     const float* vb = v + (long long)b * nk * HD + h * D;
+    if (tid < ATT_ROWS * V4) {
+      const int i = min(row0 + tid / V4, nq - 1);       // rows past the end recompute the last row (not stored)
+      qreg = __ldg(reinterpret_cast<const float4*>(q + ((long long)b * nq + i) * HD + h * D + (tid % V4) * 4));
+    }
 #pragma unroll
     for (int u = 0; u < PF; ++u) {
       const int e = tid + u * ATB_THREADS;
@@ -185,6 +191,7 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
         *reinterpret_cast<float4*>(Vs + j * S + c) = vreg[u];
       }
     }
+    if (tid < ATT_ROWS * V4) *reinterpret_cast<float4*>(Qs + tid * 4) = qreg;
     __syncthreads();
     if (b + 1 < b_end) prefetch(b + 1);
 
@@ -193,8 +200,7 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
       float qr[RW][D], m[RW], l[RW], acc[RW][D];
 #pragma unroll
       for (int w = 0; w < RW; ++w) {
-        const int i = min(row0 + r + w, nq - 1);      // rows past the end recompute the last row (not stored)
-        load_row<D>(qr[w], q + ((long long)b * nq + i) * HD + h * D);
+        load_row<D>(qr[w], Qs + (r + w) * D);
         m[w] = -INFINITY; l[w] = 0.f;
 #pragma unroll
         for (int c = 0; c < D; ++c) { qr[w][c] *= sc; acc[w][c] = 0.f; }
@@ -371,7 +377,7 @@ static int launch_fwd(const float* q, const float* k, const float* v, const floa
   constexpr int KSv = ATB_WARPS / (ATT_ROWS / RWv) >= 1 ? ATB_WARPS / (ATT_ROWS / RWv) : 1;
   const int nk_pad = nk + ((33 - (nk & 31)) & 31);           // row stride = 1 mod 32: the RW rows of a pass hit distinct banks
   const size_t smem_b = sizeof(float) * (2 * (size_t)nk * KPad<D>::stride + (size_t)KSv * ATT_ROWS * (D + 2) +
-                                         (size_t)ATT_ROWS * nk_pad);
+                                         (size_t)ATT_ROWS * D + (size_t)ATT_ROWS * nk_pad);
   const bool big_pos = pos != nullptr && (size_t)heads * nq * nk * sizeof(float) > (16u << 20) && B >= 4;
   if (big_pos && smem_b <= 226 * 1024 && (long long)nk * (D / 4) <= 2560) {
     const int blocks_xy = cdiv(nq, ATT_ROWS) * heads;

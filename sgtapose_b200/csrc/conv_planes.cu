@@ -48,6 +48,7 @@ constexpr int S_TMA_WARPS = 4;                           // bulk copies issued b
                                                          // each, tests/cuda/tma_bw_probe.cu): spread them over 4
 constexpr int S_EPI_NH = 2;                              // epilogue warps per TMEM lane quadrant (each takes half the columns)
 constexpr int S_THREADS = (S_TMA_WARPS + 1 + 4 * S_EPI_NH) * 32;    // TMA warps, MMA, epilogue warps
+constexpr int S_MAX_SB = 24;                             // B ring slots (resident weights: one per K block)
 
 enum { PROD_DCN = 0, PROD_STRIDE = 1, PROD_SMALLC = 2 };
 
@@ -613,14 +614,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   unsigned char* sA = smem + p.stg_bytes;
   unsigned char* sB = sA + (size_t)p.SA * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.SB * b_stage);
-  uint64_t *a_full = bars, *a_empty = bars + 8, *b_full = bars + 16, *b_empty = bars + 24;
+  uint64_t *a_full = bars, *a_empty = bars + 8, *b_full = bars + 56, *b_empty = bars + 56 + S_MAX_SB;
   uint64_t *acc_full = bars + 32, *acc_empty = bars + 34;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
   uint64_t *slot_full = bars + 38, *slot_empty = bars + 44;     // fp32 mode: up to 6 D0 band slots (acc_empty = D1 buffers)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], NS); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], NS); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < S_MAX_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * S_EPI_NH); }
     for (int s = 0; s < 6; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4 * S_EPI_NH); }
     fence_mbar_init();
@@ -667,7 +669,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
             for (int dx = 0; dx < ntap_b; ++dx) {
               if (((sb + 2) & (S_TMA_WARPS - 1)) == warp) {
                 mbar_wait(&b_empty[sb], bph);
-                if (skipB) mbar_arrive(&b_full[sb]);
+                // resident weights (SB == nkb): every slot is filled during this CTA's first tile and only re-armed later
+                if (skipB || (p.b_resident && t != (int)blockIdx.x)) mbar_arrive(&b_full[sb]);
                 else {
                   const int tap = band * ntap_b + dx;
                   mbar_arrive_expect_tx(&b_full[sb], b_stage);
@@ -1607,10 +1610,26 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   // whole weight prefetch, so the epilogue's store staging is only taken when SB >= 4 still fits
   const int min_sb = p.taps == 9 ? 3 : 2;
   int fixed = 0, SA = 0, SB = 0;
+  // Resident weights: when one N tile covers Cout and all K blocks fit next to >= 2 A stages, the B ring gets one slot
+  // per K block and is filled once per CTA instead of once per tile (64 -> 64 3x3: 147 KB of weights per 128-row tile
+  // otherwise -- more L2 -> SM traffic than the A bands).  Debug flag 2048 disables it.
+  p.b_resident = 0;
+  if (p.n_tiles == 1 && p.nkb <= S_MAX_SB && p.nkb >= min_sb && !(p.dbg & 2048)) {
+    const int stg = (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 16384 * NS : 0;
+    const int fx = 1024 + 1024 + stg;
+    if (2 * a_stage + p.nkb * b_stage + fx <= SMEM_LIMIT) {
+      p.b_resident = 1;
+      p.stg_bytes = stg;
+      fixed = fx;
+      SB = p.nkb;
+      SA = (SMEM_LIMIT - fx - SB * b_stage) / a_stage;
+      if (SA > 6) SA = 6;
+    }
+  }
   // (fp32 mode: measured no gain -- the hi/lo tile needs 32 KB that the weight ring uses better)
-  for (int with_stg = (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 1 : 0; with_stg >= 0; --with_stg) {
+  for (int with_stg = p.b_resident ? -1 : (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 1 : 0; with_stg >= 0; --with_stg) {
     p.stg_bytes = with_stg ? 16384 * NS : 0;
-    fixed = 1024 + 512 + p.stg_bytes;
+    fixed = 1024 + 1024 + p.stg_bytes;
     SB = 4; SA = 3;
     while (SB > min_sb && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SB;
     while (SA > 1 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SA;
@@ -1619,8 +1638,10 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
     if (!with_stg) { set_error("conv_shift: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
   }
   // spend what is left on deeper rings
-  while (SA < 6 && (SA + 1) * a_stage + SB * b_stage + fixed <= SMEM_LIMIT && SA <= SB) ++SA;
-  while (SB < 8 && SA * a_stage + (SB + 1) * b_stage + fixed <= SMEM_LIMIT) ++SB;
+  if (!p.b_resident) {
+    while (SA < 6 && (SA + 1) * a_stage + SB * b_stage + fixed <= SMEM_LIMIT && SA <= SB) ++SA;
+    while (SB < 8 && SA * a_stage + (SB + 1) * b_stage + fixed <= SMEM_LIMIT) ++SB;
+  }
   p.SA = SA; p.SB = SB;
   const int smem = SA * a_stage + SB * b_stage + fixed;
   static int sms = 0;

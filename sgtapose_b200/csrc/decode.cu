@@ -321,7 +321,7 @@ decode_peaks_kernel(const float* __restrict__ hm, const float* __restrict__ reg,
 // map by cp.async (2 CTAs/SM instead of 3: 0.37 ms vs 0.30 ms); 384-thread CTAs (12 warps x 3 CTAs, 56
 // registers, no spills in the blur passes: 0.33 ms).
 // ---------------------------------------------------------------------------------------
-struct GaussWF { float w[25]; };
+struct GaussWF { float w[25]; int full_map; };     // full_map != 0: blur every pixel (test hook: sgta_debug_flags bit 12)
 constexpr int SEG = 12;
 constexpr float ERR_BOUND = 80.f * 5.9604644775390625e-08f;   // 80 * 2^-24, see the derivation above
 
@@ -396,6 +396,7 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
                         const __grid_constant__ GaussWF gf, int C, int h, int w, int plane_floats) {
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ int s_count, s_nund, s_nacc, s_min_ok, s_nhot, s_finite;
+  __shared__ int s_box[4];                              // active rows [0..1] / columns [2..3] (see "active box" below)
   __shared__ int s_hot[HOT_CAP];                        // pass-2 items (12 pixels each) that may hold a pixel above the threshold
   __shared__ float s_max[8];
   __shared__ int s_list[UND_CAP];                       // undecided pixels (row-major position)
@@ -408,7 +409,10 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
   float* bufA = reinterpret_cast<float*>(dsm);
   float* bufB = bufA + plane_floats;
   Cand* cands = reinterpret_cast<Cand*>(bufB);          // aliases bufB (dead once the scans are done)
-  if (tid == 0) { s_count = 0; s_nund = 0; s_nacc = 0; s_min_ok = 1; s_nhot = 0; s_finite = 1; }
+  if (tid == 0) {
+    s_count = 0; s_nund = 0; s_nacc = 0; s_min_ok = 1; s_nhot = 0; s_finite = 1;
+    s_box[0] = h; s_box[1] = -1; s_box[2] = w; s_box[3] = -1;
+  }
   __syncthreads();
 
   // phase 0
@@ -445,6 +449,7 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
   }
   m = warp_max(m);
   if (lane == 0) s_max[warp] = m;
+  for (int x = tid; x < w; x += 256) bufB[h + x] = 0.f;         // column maxima of the active-box test (bufB is still free)
   if (!pos) s_min_ok = 0;                                       // benign race: every writer stores 0
   if (!fin) s_finite = 0;
   __syncthreads();
@@ -463,6 +468,57 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
     }
   };
 
+  // Active box.  Only pixels whose blurred value may reach the 0.01 threshold can be peaks, and for a non-negative
+  // map the blur (weights >= 0, sum 1 in either pass) is bounded by the blurred row / column maxima:
+  //     blur(y, x) <= sum_i w_i * rowmax[refl(y + i)] =: R(y),   blur(y, x) <= sum_j w_j * colmax[refl(x + j)] =: C(x).
+  // Rows with R(y) < TAU and columns with C(x) < TAU (TAU = 0.0099: 1 % below the threshold, the float32 evaluation of
+  // R / C is good to 1e-6) hold no peak and are never "undecided", so the two passes only run on the bounding box of
+  // the rest, grown by one pixel (the neighbours a comparison reads; they are below the threshold themselves, which
+  // is all the predicate needs to know about them).  A real heat map is a few blobs on a flat floor: the box is a
+  // few per cent of the map and the kernel turns from FP32-issue-bound into a read of the map.
+  int ya0 = 0, ya1 = h - 1, xa0 = 0, xa1 = w - 1;               // box in which bufA will hold blurred values
+  if (PACKED && nonneg && s_finite && !gf.full_map) {
+    // (non-negative finite floats order like their bit patterns: REDUX / integer atomicMax do the reductions)
+    float* rmax = bufB;                                         // bufB is free until pass 1
+    unsigned* cmax_u = reinterpret_cast<unsigned*>(bufB + h);   // zeroed in phase 0
+    for (int y = warp; y < h; y += 8) {
+      float v = 0.f;
+      for (int x = lane; x < w; x += 32) v = fmaxf(v, bufA[y * w + x]);
+      const unsigned mu = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+      if (lane == 0) rmax[y] = __uint_as_float(mu);
+    }
+    {
+      const int G = 256 / w > 0 ? 256 / w : 1;                  // row groups: (group, column) per thread
+      for (int e = tid; e < G * w; e += 256) {
+        const int g = e / w, x = e - g * w;
+        const int y0 = g * h / G, y1 = (g + 1) * h / G;
+        float v = 0.f;
+#pragma unroll 8
+        for (int y = y0; y < y1; ++y) v = fmaxf(v, bufA[y * w + x]);
+        atomicMax(cmax_u + x, __float_as_uint(v));
+      }
+    }
+    const float* cmax = bufB + h;
+    __syncthreads();
+    constexpr float TAU = 0.0099f;
+    for (int e = tid; e < h + w; e += 256) {
+      const bool isrow = e < h;
+      const int i0 = isrow ? e : e - h, n = isrow ? h : w;
+      const float* mx = isrow ? rmax : cmax;
+      float r = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2 * GR + 1; ++t) r = fmaf(gf.w[t], mx[refl(i0 - GR + t, n)], r);
+      if (r >= TAU) {
+        atomicMin(&s_box[isrow ? 0 : 2], i0);
+        atomicMax(&s_box[isrow ? 1 : 3], i0);
+      }
+    }
+    __syncthreads();
+    ya0 = max(s_box[0] - 1, 0); ya1 = min(s_box[1] + 1, h - 1);
+    xa0 = max(s_box[2] - 1, 0); xa1 = min(s_box[3] + 1, w - 1);
+    if (s_box[1] < 0 || s_box[3] < 0) { ya0 = 0; ya1 = -1; xa0 = 0; xa1 = -1; }    // nothing can reach the threshold
+  }
+
   if (PACKED) {
     // h, w even and >= SEG2 + 2*GR (launcher).  Pass 1: lane = two adjacent columns (one LDS.64 of the dense
     // map per input row); its output goes to bufB interleaved by ROW PAIR, [h/2][w|1] float2 = (row 2j, row 2j+1),
@@ -472,9 +528,16 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
     for (int t = 0; t < 2 * GR + 1; ++t) w2[t] = make_float2(gf.w[t], gf.w[t]);
     float2* tmpI = reinterpret_cast<float2*>(bufB);
     const int wh = w >> 1, hh = h >> 1;
-    const int nsy = (h + SEG2 - 1) / SEG2;
-    for (int it = tid; it < nsy * wh; it += 256) {
-      const int sg = it / wh, x = 2 * (it - sg * wh), y0 = sg * SEG2;
+    // items of the active box only: row segments that hold a box row x column pairs within GR of a box column
+    // (pass-2 items are whole column segments: pass 1 covers every column they read, so that every value pass 2
+    // writes -- also the ones outside the box -- is a true blurred value)
+    const bool any = ya1 >= ya0;
+    const int sgy0 = ya0 / SEG2, nsy = any ? ya1 / SEG2 - sgy0 + 1 : 0;
+    const int sgx0 = xa0 / SEG2, nsx = any ? xa1 / SEG2 - sgx0 + 1 : 0;
+    const int xp0 = max(sgx0 * SEG2 - GR, 0) >> 1;
+    const int nxp = any ? (min((sgx0 + nsx) * SEG2 - 1 + GR, w - 1) >> 1) - xp0 + 1 : 0;
+    for (int it = tid; it < nsy * nxp; it += 256) {
+      const int sg = sgy0 + it / nxp, x = 2 * (xp0 + it % nxp), y0 = sg * SEG2;
       const float2* col = reinterpret_cast<const float2*>(bufA + x);    // row stride w floats = w/2 float2
       float2 a2[SEG2];
       if (y0 >= GR && y0 + SEG2 + GR <= h) packed_taps<true>(col, wh, y0 - GR, h, w2, a2);
@@ -489,9 +552,9 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
       }
     }
     __syncthreads();
-    const int nsx = (w + SEG2 - 1) / SEG2;
-    for (int it = tid; it < nsx * hh; it += 256) {
-      const int sg = it / hh, yp = it - sg * hh, x0 = sg * SEG2;
+    const int yp0 = ya0 >> 1, nyp = any ? (ya1 >> 1) - yp0 + 1 : 0;
+    for (int it = tid; it < nsx * nyp; it += 256) {
+      const int sg = sgx0 + it / nyp, yp = yp0 + it % nyp, x0 = sg * SEG2;
       const float2* row = tmpI + yp * wp;
       float2 a2[SEG2];
       if (x0 >= GR && x0 + SEG2 + GR <= w) packed_taps<true>(row, 1, x0 - GR, w, w2, a2);
@@ -619,17 +682,20 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
         if (x < w) test_pixel(y0 + j / IC, x);
       }
     } else {
-      for (int y = warp; y < h; y += 8) {
+      // (outside the active box bufA still holds the raw map; in the float64 round it is valid everywhere, but no
+      // pixel out there can pass the threshold either way)
+      const int xe = xa1 + 1;
+      for (int y = ya0 + warp; y <= ya1; y += 8) {
         const float* rowp = bufA + y * wp;
-        for (int x0 = lane; x0 < w; x0 += 128) {
+        for (int x0 = xa0 + lane; x0 < xe; x0 += 128) {
           // threshold test of four pixels per lane first
           float v4[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v4[j] = x0 + 32 * j < w ? rowp[x0 + 32 * j] : 0.f;
+          for (int j = 0; j < 4; ++j) v4[j] = x0 + 32 * j < xe ? rowp[x0 + 32 * j] : 0.f;
           unsigned pass = 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (x0 + 32 * j < w && !(v4[j] < BLUR_THRESH - fmaf(er, v4[j], ea))) pass |= 1u << j;
+            if (x0 + 32 * j < xe && !(v4[j] < BLUR_THRESH - fmaf(er, v4[j], ea))) pass |= 1u << j;
           while (pass) {
             const int x = x0 + 32 * (__ffs(pass) - 1);
             pass &= pass - 1;
@@ -893,6 +959,9 @@ static int check_peaks_args(const void* hm, void* scores, void* inds, void* xs, 
   return SGTA_OK;
 }
 
+static int g_decode_full_map = 0;
+extern "C" int sgta_decode_full_map(int on) { int old = g_decode_full_map; g_decode_full_map = on ? 1 : 0; return old; }
+
 extern "C" int sgta_decode_peaks(const void* hm, const void* reg, const void* tracking, void* scores,
                                  void* inds, void* xs, void* ys, void* cts_wreg, void* trk,
                                  const double* gauss_w, int B, int C, int h, int w, void* stream) {
@@ -901,6 +970,7 @@ extern "C" int sgta_decode_peaks(const void* hm, const void* reg, const void* tr
   GaussW gw;
   GaussWF gf;
   for (int i = 0; i < 25; ++i) { gw.w[i] = gauss_w[i]; gf.w[i] = (float)gauss_w[i]; }
+  gf.full_map = g_decode_full_map;
   // one plane: h rows of odd stride, at least the 512 block-reduction candidates that alias the second one
   size_t plane = (size_t)h * (w | 1);
   if (plane * sizeof(float) < sizeof(Cand) * 512) plane = sizeof(Cand) * 512 / sizeof(float);

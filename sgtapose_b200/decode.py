@@ -47,6 +47,11 @@ def recheck_count(reset=True):
     return int(n.value)
 
 
+def full_map(on):
+    """Test hook: make the production decode blur every pixel instead of the active box only; returns the old setting."""
+    return bool(_lib.load().sgta_decode_full_map(int(bool(on))))
+
+
 def peaks_decode(hm, reg=None, tracking=None, exact64=False):
     """One launch of the live decode.  Returns dict of device tensors:
     scores [B,C] f32, inds/xs/ys [B,C] i64, cts_wreg [B,C,2] f32, tracking [B,C,2] f32|None.

@@ -377,6 +377,56 @@ def test_decode_peaks_full_size_production_equals_exact64():
     assert (a["scores"] >= 0).float().mean() > 0.5                 # most keypoints found
 
 
+def test_decode_active_box_equals_full_map():
+    """The production decode only blurs the bounding box of the rows / columns whose blurred maxima can reach the
+    0.01 threshold.  Same outputs as blurring every pixel (test hook) and as the oracle, on maps that stress the
+    box: blobs on the borders and in corners, several blobs, a blob that barely clears the threshold, a floor
+    just below / just above the cut-off, an empty map."""
+    from sgtapose_b200 import decode
+    h = w = 96
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+
+    def blob(cx, cy, amp=0.9, s=2.0):
+        return amp * torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+
+    g = torch.Generator().manual_seed(9)
+    noise = lambda a: a * torch.rand(h, w, generator=g)
+    maps = [
+        blob(0, 0) + noise(0.004), blob(95, 0) + noise(0.004), blob(47.5, 95) + noise(0.004), blob(95, 48) + noise(0.004),
+        blob(10, 12) + blob(80, 85, amp=0.6) + noise(0.005),            # two far blobs: one big box
+        blob(40, 40, amp=0.04) + noise(0.002),                         # blurred summit ~0.012: just above the threshold
+        blob(40, 40, amp=0.03) + noise(0.002),                         # ... ~0.009: just below
+        torch.full((h, w), 0.0098) + blob(70, 20, amp=0.5),            # floor below the cut-off
+        torch.full((h, w), 0.00995) + blob(70, 20, amp=0.5),           # floor between the cut-off and the threshold: full box
+        noise(0.009), torch.zeros(h, w), blob(13, 13) + blob(14, 13) + noise(0.001),
+        blob(30, 60, amp=1.0, s=6.0) + noise(0.003), noise(0.02),
+    ]
+    hm = torch.stack(maps)[None].repeat(2, 1, 1, 1).clamp(0, 1)
+    hm[1] = hm[1].flip(-1)
+    ref = odec.dream_generic_decode(hm.numpy())
+    old = decode.full_map(False)
+    try:
+        a = decode.peaks_decode(hm.to(DEV))
+        decode.full_map(True)
+        b = decode.peaks_decode(hm.to(DEV))
+    finally:
+        decode.full_map(old)
+    _same_decode(a, b)
+    for k in ("xs", "ys", "inds", "scores"):
+        assert np.array_equal(a[k].cpu().numpy(), ref[k]), k
+    # non-square even-sized maps take the same path
+    hm2, _ = synth_heatmaps_rect()
+    ref2 = odec.dream_generic_decode(hm2.numpy())
+    a2 = decode.peaks_decode(hm2.to(DEV))
+    for k in ("xs", "ys", "inds", "scores"):
+        assert np.array_equal(a2[k].cpu().numpy(), ref2[k]), k
+
+
+def synth_heatmaps_rect():
+    from sgtapose_b200 import synth
+    return synth.synthetic_heatmaps(3, 5, 64, 120, seed=21, noise=0.004, missing_every=3)
+
+
 def test_nms_topk_softargmax_golden(golden):
     from sgtapose_b200 import decode
     g = golden("decode.npz")
