@@ -472,7 +472,7 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
     __syncwarp();
     if (lane == 0) mbar_arrive(&d1_empty[rd.i]);
     rd.next();
-    if (p.dbg & 4) continue;
+    if (p.dbg & (4 | 8192)) continue;                       // 8192: drain TMEM but skip the math and the stores
     EpiRow e;
     epi_row_setup(p, p.tile2d ? tile_row_m(p, t / p.n_tiles, q * 32 + lane) : m0 + q * 32 + lane, e);
     if (p.epi == SGTA_EPI_STEM || p.epi == SGTA_EPI_STEM_SP) {
@@ -1111,8 +1111,11 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
           for (int kb = 0; kb < nkb; ++kb) {
             const int blk = PROD == PROD_SMALLC ? kb : tap * p.KC + kc;
             mbar_wait(&empty[s], ph);
-            mbar_arrive_expect_tx(&full[s], b_bytes);
-            bulk_g2s(ring + (size_t)s * stage_bytes + a_bytes, wt + (size_t)blk * b_bytes, b_bytes, &full[s]);
+            if (p.dbg & 2) mbar_arrive(&full[s]);
+            else {
+              mbar_arrive_expect_tx(&full[s], b_bytes);
+              bulk_g2s(ring + (size_t)s * stage_bytes + a_bytes, wt + (size_t)blk * b_bytes, b_bytes, &full[s]);
+            }
             if (++s == p.SA) { s = 0; ph ^= 1u; }
             if (++tap == 9) { tap = 0; ++kc; }
           }

@@ -24,7 +24,7 @@ for ns in ns_list:
         spec = P.ConvSpec(P.weight_matrix(w), torch.ones(Co, device=DEV), torch.zeros(Co, device=DEV), Ci, k, 1, ns, P.ACT_RELU)
         fl = 2.0 * B * H * H * Co * Ci * k * k
         out = []
-        for flags in (0, 8, 4, 7):
+        for flags in (0, 8192, 4, 7):
             _lib.load().sgta_debug_flags(flags | NTF)
             us = bench(lambda: P.conv(spec, xb.full, yb.full))
             out.append("f%d %7.1fus %6.1fTF" % (flags, us, fl / us / 1e6))

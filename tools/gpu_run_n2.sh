@@ -1,2 +1,9 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "n2 rc=$?"; tail -c 1500 gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?"; tail -5 gpurun_out/bench_n2.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1])
+print('n_gpus', d['n_gpus'], 'frames/s', round(d['value'],1), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1))
+print('parity', d.get('parity_checked'))
+print('pipeline', json.dumps(d.get('pipeline'))[:1200])
+PY
