@@ -291,6 +291,8 @@ def run_ours(args):
     if engine_path and world == 1 and not args.no_extras and args.mode == "fp32":
         # the same step in bf16 mode (the precision north_star states the tensor-pipe target in), next to the fp32 headline
         extra.update(bf16_leg(sd, opt, B, dev, resident, args.steps))
+        if not args.skip_dead_levels:
+            extra.update(skip_dead_leg(sd, opt, B, dev, resident, args.steps))
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -475,6 +477,26 @@ def bf16_leg(sd, opt, B, dev, resident, steps):
                               "peak_source": which + " bf16 sustained", "traffic_source": src,
                               "parity": "bf16 mode is validated per kernel and end to end in tests/ (stated looser bound, "
                                         "DESIGN.md 4); the headline `value` is the fp32 mode"}}
+
+
+def skip_dead_leg(sd, opt, B, dev, resident, steps):
+    """The same fp32 step without the structure-prior fusion of levels 0 and 1.  Their fused maps never reach the output
+    (DLAUp starts at level 2, dla.py:1548: the reference computes them and drops them), so the outputs are identical
+    bit for bit; reported beside the headline, which keeps the reference's full work."""
+    from sgtapose_b200 import engine
+    eng = engine.InferenceEngine(sd, opt, batch=B, size=S, mode="fp32", device=dev, fuse_sigmoid=True, skip_dead_levels=True)
+    for _ in range(3):
+        eng.infer(*resident)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.infer(*resident)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del eng
+    return {"value_skip_dead_levels": B * steps / (ms / 1e3), "ms_per_step_skip_dead_levels": ms / steps}
 
 
 def sequence_pipeline(engs, dev, world, rank, frames):

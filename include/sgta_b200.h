@@ -291,6 +291,15 @@ int sgta_planes_superpixels(const sgta_planes* sc, const sgta_planes* sp, int to
 int sgta_preprocess(const void* img_u8, void* out, void* out_u8, const double* trans, int n_trans,
                     const float* mean3, const float* std3, int B, int h, int w, int H, int W, void* stream);
 
+/* Post-processing of the live decode on the device: dream_generic_post_process
+ * (sgtapose/lib/utils/post_process.py:93-117), merge_outputs (lib/sgta_detector.py:955-961) and _get_final_kps
+ * (:608-651, is_ct branch) for one detection per class.
+ *   scores [B,K] f32, cts_wreg [B,K,2] f32 (network-output pixels) DEVICE
+ *   kps_raw [B,K,2] f64 DEVICE: raw-image pixels, `missing` where score < / <= out_thresh
+ *   trans_inv6 HOST, 6 floats: get_affine_transform(c, s, 0, (w, h), inv=1).astype(float32), row-major 2x3 */
+int sgta_post_process(const void* scores, const void* cts_wreg, void* kps_raw, const float* trans_inv6,
+                      float out_thresh, double missing, int B, int K, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Host-side pose refinement (no device work): the `LM` entry of the reference's
  * binary-only rf_tools/libtestso_final.so, bound at sgtapose/rf_tools/LM.py:10 and called from

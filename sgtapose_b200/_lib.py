@@ -67,6 +67,7 @@ SIGNATURES = {
     "sgta_token_mlp": (_I, [_P] * 15 + [_I] * 4 + [_F, _P]),
     "sgta_token_linear": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
     "sgta_preprocess": (_I, [_P, _P, _P, _c.POINTER(_c.c_double), _I, _c.POINTER(_F), _c.POINTER(_F)] + [_I] * 5 + [_P]),
+    "sgta_post_process": (_I, [_P, _P, _P, _c.POINTER(_F), _F, _c.c_double, _I, _I, _P]),
     "sgta_lm_refine": (_I, [_c.POINTER(_c.c_double)] * 6 + [_I]),
     "sgta_render_priors": (_I, [_P, _P, _P, _P, _c.POINTER(_F)] + [_I] * 6 + [_P]),
 }

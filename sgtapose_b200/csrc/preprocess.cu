@@ -73,9 +73,38 @@ static void invert_affine(const double* M, double* m) {
   m[2] = b1; m[5] = b2;
 }
 
+// Post-processing of the live decode (one detection per class): dream_generic_post_process (lib/utils/post_process.py:93-117:
+// detections with score < out_thresh dropped, ct_wreg mapped to raw-image pixels with the float32 inverse output
+// affine, image.py:20-26), merge_outputs (sgta_detector.py:955-961: score > out_thresh) and _get_final_kps (:608-651,
+// is_ct branch: best score per class).  One thread per (clip, keypoint); float32 arithmetic like the reference's
+// np.dot of float32 operands, result widened to float64 (the reference's kps array).
+__global__ void post_process_kernel(const float* __restrict__ scores, const float* __restrict__ cts, double* __restrict__ kps,
+                                    float t00, float t01, float t02, float t10, float t11, float t12, float thresh,
+                                    double missing, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float s = scores[e], x = cts[2 * e], y = cts[2 * e + 1];
+  const bool keep = s >= thresh && s > thresh;
+  // dot([t0, t1, t2], [x, y, 1]): products summed left to right, no contraction
+  const float rx = __fadd_rn(__fadd_rn(__fmul_rn(t00, x), __fmul_rn(t01, y)), t02);
+  const float ry = __fadd_rn(__fadd_rn(__fmul_rn(t10, x), __fmul_rn(t11, y)), t12);
+  kps[2 * e] = keep ? (double)rx : missing;
+  kps[2 * e + 1] = keep ? (double)ry : missing;
+}
+
 }  // namespace sgta
 
 using namespace sgta;
+
+extern "C" int sgta_post_process(const void* scores, const void* cts_wreg, void* kps_raw, const float* trans_inv6,
+                                 float out_thresh, double missing, int B, int K, void* stream) {
+  SGTA_REQUIRE(scores && cts_wreg && kps_raw && trans_inv6 && B > 0 && K > 0, "sgta_post_process: bad arguments");
+  const int n = B * K;
+  post_process_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      (const float*)scores, (const float*)cts_wreg, (double*)kps_raw, trans_inv6[0], trans_inv6[1], trans_inv6[2],
+      trans_inv6[3], trans_inv6[4], trans_inv6[5], out_thresh, missing, n);
+  return check_launch("post_process_kernel");
+}
 
 extern "C" int sgta_preprocess(const void* img_u8, void* out, void* out_u8, const double* trans, int n_trans,
                                const float* mean3, const float* std3, int B, int h, int w, int H, int W,

@@ -104,6 +104,21 @@ def post_process_batch(scores, cts_wreg, trans_inv, out_thresh):
     return out
 
 
+def post_process_device(scores, cts_wreg, trans_inv, out_thresh, out=None):
+    """`post_process_batch` on the device (sgta_post_process): scores [B,K] / cts_wreg [B,K,2] float32 CUDA tensors ->
+    kps_raw [B,K,2] float64 CUDA tensor (MISSING where nothing passed `out_thresh`)."""
+    import ctypes
+    from . import _lib
+    B, K = scores.shape
+    scores, cts_wreg = scores.contiguous().float(), cts_wreg.contiguous().float()
+    if out is None:
+        out = torch.empty(B, K, 2, device=scores.device, dtype=torch.float64)
+    t6 = (ctypes.c_float * 6)(*[float(v) for v in np.asarray(trans_inv, np.float32).reshape(6)])
+    _lib.call("sgta_post_process", _lib.ptr(scores), _lib.ptr(cts_wreg), _lib.ptr(out), t6, float(out_thresh),
+              float(MISSING), B, K, _lib.stream())
+    return out
+
+
 def is_pnp_pose(prev_pos, prev_projs, next_pos, prev_projs_all, camera_K):
     """`is_pnp` plus the pose it solved: -> (prev_kp_projs, next_kp_projs_est, pose [7] = t xyz + quaternion xyzw, or
     None when PnP failed).  The pose of frame f-1's detections is what the sequence runner reports per frame."""
@@ -150,7 +165,9 @@ class LockstepDetector:
         self._c_out = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64).pin_memory()
         self._d_in = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64, device=dev)
         self._d_out = torch.zeros(2, self.B, self.n_kp, 2, dtype=torch.float64, device=dev)
-        self._res = torch.zeros(self.B, self.n_kp, 3, dtype=torch.float32).pin_memory()
+        self._res = torch.zeros(self.B, self.n_kp, 2, dtype=torch.float64).pin_memory()     # kps_raw
+        self._res_sc = torch.zeros(self.B, self.n_kp, dtype=torch.float32).pin_memory()     # scores
+        self._d_res = torch.zeros(self.B, self.n_kp, 2, dtype=torch.float64, device=dev)
         self._done = torch.cuda.Event()
         self._begun = False
         self.reset()
@@ -185,9 +202,6 @@ class LockstepDetector:
             return np.concatenate([t, q]) if ok else None
         res = list(self.pool.map(one, range(self.B))) if self.pool else [one(b) for b in range(self.B)]
         return np.stack([np.full(7, np.nan) if r is None else r for r in res])
-
-    def _post(self, scores, cts_wreg):
-        return post_process_batch(scores, cts_wreg, self.trans_inv, self.out_thresh)
 
     # ------------------------------------------------------------------ one frame of every clip
     def step(self, images, x3d_prev=None, x3d_next=None):
@@ -245,9 +259,12 @@ class LockstepDetector:
             PR.render_priors(self._d_in[1], self._d_out[1], self.S, self.q, hm=inp["repro_hm"], hm_cls=inp["repro_hm_cls"])
         t1 = time.perf_counter()
         dets = eng.infer()
-        packed = torch.cat([dets["scores"].view(self.B, self.n_kp, 1),
-                            dets["cts_wreg"].view(self.B, self.n_kp, 2)], dim=2)
-        self._res.copy_(packed, non_blocking=True)
+        # post_process + merge_outputs + _get_final_kps on the device: raw-image keypoints (float64) and scores come
+        # back in two small copies
+        post_process_device(dets["scores"].view(self.B, self.n_kp), dets["cts_wreg"].view(self.B, self.n_kp, 2),
+                            self.trans_inv, self.out_thresh, out=self._d_res)
+        self._res.copy_(self._d_res, non_blocking=True)
+        self._res_sc.copy_(dets["scores"].view(self.B, self.n_kp), non_blocking=True)
         self._done.record(torch.cuda.current_stream(eng.dev))
         self.timing["host_pnp"] += t1 - t0
         self._begun = True
@@ -259,9 +276,8 @@ class LockstepDetector:
         self._begun = False
         self._done.synchronize()
         t2 = time.perf_counter()
-        r = self._res.numpy()
-        scores = r[:, :, 0].copy()
-        self.detected_kps = self._post(scores, r[:, :, 1:3])
+        scores = self._res_sc.numpy().copy()
+        self.detected_kps = self._res.numpy().copy()
         t3 = time.perf_counter()
         self.timing["host_post"] += t3 - t2
         self.timing["steps"] += 1

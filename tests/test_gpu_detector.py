@@ -90,6 +90,27 @@ def test_step_sequence_priors_and_decode(det):
     assert det.frame == 3 and det.timing["steps"] == 3
 
 
+def test_post_process_device_vs_oracle():
+    """sgta_post_process (post_process + merge_outputs + _get_final_kps on the device) vs the per-item restatement of
+    post_process.py:93-117 / sgta_detector.py:608-651, :955-961 -- bit-exact, incl. scores at and around the threshold."""
+    from sgtapose_b200 import detector
+    from sgtapose_b200 import priors as PR
+    rng = np.random.default_rng(3)
+    Bn, K = 37, 7
+    scores = rng.random((Bn, K)).astype(np.float32)
+    scores[0, :3] = [0.001, np.float32(0.001) + np.float32(1e-9), 0.00099]
+    scores[1] = -1.0                                            # the decode's "missing" score
+    cts = (rng.random((Bn, K, 2)) * 96).astype(np.float32)
+    c, s = np.array([320.0, 180.0], np.float32), 640.0
+    trans_inv = PR.get_affine_transform(c, s, 0, (96, 96), inv=1).astype(np.float32)
+    thresh = 0.001
+    got = detector.post_process_device(torch.from_numpy(scores).to(DEV), torch.from_numpy(cts).to(DEV), trans_inv, thresh).cpu().numpy()
+    for b in range(Bn):
+        want = odet.final_kps(odet.post_process_one(scores[b], cts[b], trans_inv, thresh), K)
+        assert np.array_equal(got[b], want), b
+    assert np.array_equal(got, detector.post_process_batch(scores, cts, trans_inv, thresh))   # the host form agrees
+
+
 def test_step_accepts_raw_uint8_frames(det):
     """Raw 640x360 uint8 frames pre-processed on the device == the oracle's pre_process of the same frames
     fed as float32 network inputs: identical input buffer and identical detections."""
