@@ -34,7 +34,10 @@ def test_post_process_matches_reference_loops(det):
     scores[0, 2] = -1.0
     scores[1] = 0.0005                                   # below out_thresh = 0.001
     cts = rng.uniform(0, S // 4, size=(B, 7, 2)).astype(np.float32)
-    got = det._post(scores, cts)
+    from sgtapose_b200 import detector
+    got = detector.post_process_device(torch.from_numpy(scores).to(DEV), torch.from_numpy(cts).to(DEV), det.trans_inv,
+                                       det.out_thresh).cpu().numpy()
+    assert np.array_equal(got, detector.post_process_batch(scores, cts, det.trans_inv, det.out_thresh))
     for b in range(B):
         want = odet.final_kps(odet.post_process_one(scores[b], cts[b], det.trans_inv, det.out_thresh), 7)
         assert np.array_equal(got[b], want), b
