@@ -1,25 +1,28 @@
 """Compiled inference engine: the whole per-frame forward as a static plan of hand-written
-sm_100a kernels over NHWC buffers, optionally captured in one CUDA graph.
+sm_100a kernels over zero-bordered "planes" buffers (planes.py), captured in one CUDA graph.
 
 Same parameters, same math and same outputs as the module tree in networks.py (which mirrors
 reference sgtapose/lib/model/networks/dla.py:1505-1554 + base_model.py:170-200); what changes
 is the execution:
 
   * eval-mode BatchNorm, conv bias and ReLU are folded into the epilogue of the producing
-    tcgen05 implicit-GEMM kernel (conv_umma.cu); residual adds too;
+    tcgen05 implicit-GEMM kernel (csrc/conv_planes.cu); residual adds too;
   * the previous-frame and current-frame passes of the shared DLA-34 base (dla.py:1506-1507)
     run as ONE batch of 2B images; the two 7x7 stems (image + heat-map, dla.py:325-331) are
-    one GEMM with a dual-ReLU epilogue;
+    one GEMM over super-pixels of 4 output pixels with a dual-ReLU epilogue, and level0 is a
+    plain 64 -> 64 shift-GEMM over that super-pixel view;
   * Root concatenations (dla.py:169) are zero-copy: producers write channel slices of the
-    concat buffer (pixel-stride arguments of the C ABI);
-  * every DeformConv = offset/mask conv (N=27 padded to 32, fp32 out) + the fused
+    concat buffer (views of the C ABI);
+  * every DeformConv = offset/mask conv (N=27 padded to 32, fp32 rows out) + the fused
     bilinear-gather DCN GEMM; the depth-wise up-sampler and the IDAUp skip add are one kernel;
-  * token selection, gather, attention core, write-back and decode never leave the device;
+  * token selection, gather, the Linear layers on token rows, attention core, token MLP, write-back
+    and decode never leave the device and are all this library's kernels;
   * the three head convs 64->256 run as one 64->768 GEMM; the 1x1 output convs write NCHW fp32
     directly (optionally with the detector's sigmoid, sgta_detector.py:854-862, fused).
 
-mode="fp32": fp32 activations, F32X3 split-bf16 MMAs (parity bound 1e-3 relative);
-mode="bf16": bf16 activations and MMAs, fp32 accumulate (stated looser bound, DESIGN.md).
+mode="fp32": fp32 activations as fp16 hi + lo planes, 3 tensor-core MMAs per K step, band-drain
+             accumulation (parity bound 1e-3 relative);
+mode="bf16": bf16 activations and MMAs, fp32 accumulate (stated looser bound, DESIGN.md 4).
 """
 import torch
 
