@@ -1,3 +1,5 @@
+# compute-sanitizer (memcheck, then racecheck on the shared-memory heavy kernels) over the round-2 kernels' parity tests
 mkdir -p gpurun_out
-timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py tests/test_gpu_preprocess.py -x -q -k "decode_peaks_vs_oracle or recheck_paths or warp_u8 or pre_process_matches" > gpurun_out/san_mem.log 2>&1; echo "memcheck rc=$?"; grep -c "Invalid\|Error" gpurun_out/san_mem.log; tail -4 gpurun_out/san_mem.log
-timeout 420 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py -x -q -k "recheck_paths" > gpurun_out/san_race.log 2>&1; echo "racecheck rc=$?"; grep -c "hazard\|Race" gpurun_out/san_race.log; tail -4 gpurun_out/san_race.log
+K="token_linear or superpixel or post_process or active_box or (dcn_planes and (cfg0 or cfg5 or cfg6)) or conv_shift_vs_torch and (cfg0 or cfg4) or attention_core_vs_torch and 63"
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 5 python -m pytest tests/test_gpu_planes.py tests/test_gpu_ops.py tests/test_gpu_detector.py -m gpu -x -q -k "$K" > gpurun_out/san_mem.log 2>&1; echo "memcheck rc=$?"; tail -6 gpurun_out/san_mem.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 5 python -m pytest tests/test_gpu_ops.py tests/test_gpu_detector.py -m gpu -x -q -k "token_linear or active_box or post_process_device" > gpurun_out/san_race.log 2>&1; echo "racecheck rc=$?"; tail -6 gpurun_out/san_race.log
