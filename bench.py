@@ -275,6 +275,17 @@ def run_ours(args):
         fam, fam_total = time_kernel_families(eager_pass)
         extra["kernel_families"] = {"per_step": fam, "serialised_ms": round(fam_total, 3),
                                     "note": "one un-graphed step, CUDA events around every C-ABI call"}
+        # the dominant family by time: all plain convolutions (base x2 + heads + offset/mask convs), tensor bound
+        conv_ms = sum(v["ms"] for k, v in fam.items() if k.startswith("planes_conv"))
+        conv_gflop = (TOTAL_GFLOP_PER_FRAME - DCN_GFLOP_PER_FRAME - 1.17) * B          # SURVEY.md 8d split
+        pk, which_pk = _peaks()
+        pk_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        extra["roofline_convs"] = {"bound": "tensor", "kernel": "plain convolutions (shift-GEMM + gather-GEMM families, %d launches/step)"
+                                   % sum(v["launches"] for k, v in fam.items() if k.startswith("planes_conv")),
+                                   "achieved": conv_gflop / conv_ms, "peak": pk_tf, "unit": "TFLOP/s",
+                                   "frac": conv_gflop / conv_ms / pk_tf, "traffic": None, "ms_per_step": round(conv_ms, 3),
+                                   "peak_source": which_pk + " bf16 sustained",
+                                   "note": "algorithmic FLOPs (47.4 GFLOP per frame-pair); fp32 mode issues 3 MMAs per K step"}
         # self-check of the timed step's results (rank 0): decoded integer outputs vs the oracle's decode of the same
         # heads, and the heads of clip 0 vs the oracle's CPU forward (the cpu_baseline leg runs it anyway)
         extra["parity_checked"] = check_decode_parity(timed_heads, timed_dets)

@@ -171,6 +171,12 @@ int sgta_planes_scatter_tokens(const sgta_planes* x, int b_off, const void* ids,
 int sgta_attn_forward(const void* q, const void* k, const void* v, const void* pos,
                       void* out, int B, int heads, int nq, int nk, int d, float inv_scale,
                       void* stream);
+/* The same core with K and V given HEAD-MAJOR, [B, heads, nk, d] (written that way by sgta_token_linear_heads): the
+ * batch-looping level-0 kernel then prefetches a (sample, head) slab with coalesced loads.  Served shapes:
+ * sgta_attn_kvhm_supported(...) != 0 (d == 4, pos given, large pos block, B >= 4); q / out stay "b n (h d)". */
+int sgta_attn_kvhm_supported(int B, int heads, int nq, int nk, int d, int has_pos);
+int sgta_attn_forward_kvhm(const void* q, const void* k_hm, const void* v_hm, const void* pos, void* out,
+                           int B, int heads, int nq, int nk, int d, float inv_scale, void* stream);
 /* backward of the same core (config 5): grads w.r.t. q, k, v, pos (pos grad accumulated) */
 int sgta_attn_backward(const void* q, const void* k, const void* v, const void* pos,
                        const void* grad_out, void* grad_q, void* grad_k, void* grad_v,
@@ -257,6 +263,10 @@ int sgta_token_mlp(const void* att, const void* q, const void* fc_wt, const void
  * row-major; K1, K2 multiples of 16, N of 4; relu != 0 applies ReLU.  fp32 FMA, ascending k (replaces library SGEMMs). */
 int sgta_token_linear(const void* x1, int K1, const void* x2, int K2, const void* w, const void* bias,
                       void* y, int M, int N, int relu, void* stream);
+/* bias-free projection with a head-major result (w_k / w_v of MHCA_ein, dla.py:872-876, for sgta_attn_forward_kvhm):
+ * x [B*n_tokens, K], w [N, K] -> y [B, heads, n_tokens, N / heads] */
+int sgta_token_linear_heads(const void* x, int K, const void* w, void* y, int M, int N, int n_tokens, int heads,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Structure-prior maps: replaces the host rendering + 4 H2D copies per clip

@@ -66,6 +66,9 @@ SIGNATURES = {
     "sgta_soft_argmax": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
     "sgta_token_mlp": (_I, [_P] * 15 + [_I] * 4 + [_F, _P]),
     "sgta_token_linear": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
+    "sgta_token_linear_heads": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "sgta_attn_kvhm_supported": (_I, [_I] * 6),
+    "sgta_attn_forward_kvhm": (_I, [_P] * 5 + [_I] * 5 + [_F, _P]),
     "sgta_preprocess": (_I, [_P, _P, _P, _c.POINTER(_c.c_double), _I, _c.POINTER(_F), _c.POINTER(_F)] + [_I] * 5 + [_P]),
     "sgta_post_process": (_I, [_P, _P, _P, _c.POINTER(_F), _F, _c.c_double, _I, _I, _P]),
     "sgta_lm_refine": (_I, [_c.POINTER(_c.c_double)] * 6 + [_I]),

@@ -9,6 +9,8 @@
 // partials are merged with warp-shuffle reductions.  Nothing n x n is ever stored.
 //
 // Layout: q,k,v,out are the Linear outputs as they are, [B, n, heads*d] ("b n (h d)").
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sgta {
@@ -286,6 +288,151 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward, batch-looping variant with LANES = QUERY ROWS (D = 4: level 0, the one the engine runs).
+// Same CTA shape as attn_fwd_batched_kernel -- (32 query rows, head), pos block resident, loop over the samples --
+// but a warp's 32 lanes are the CTA's 32 query rows and the 16 warps split the KEYS: K / V rows are warp-wide
+// broadcast reads (one LDS.128 each per key and warp), the pos value of (row, key) is one conflict-free LDS per lane
+// (row stride = 1 mod 32), every lane runs its own online softmax, and nothing is reduced across lanes: the per-
+// sample epilogue is 6 stores per lane and a 16-way merge by 128 threads, where the lanes-as-keys kernel spends 100
+// shuffles + 100 adds per warp (41 % of its stall samples sat in that per-sample prologue / epilogue, ncu source page).
+// KVHM: K / V are given head-major, [B, heads, nk, D] (sgta_token_linear_heads writes them that way): the slab of a
+// (sample, head) is contiguous, so the per-sample prefetch is coalesced 16-byte loads instead of one 16-byte piece per
+// 128-byte line ("b n (h d)": a third of this kernel's stall samples were LSU-queue throttling on those gathers).
+template <int D, bool KVHM>
+__global__ void __launch_bounds__(ATB_THREADS, 1)
+attn_fwd_rows_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                     const float* __restrict__ pos, float* __restrict__ out, int B, int heads, int nq, int nk,
+                     int nk_pad, int b_per_cta, float inv_scale) {
+  static_assert(D == 4, "lanes-as-rows attention: head dim 4");
+  constexpr int PF = 5;                       // float4 pairs of K/V prefetch per thread (covers nk <= 2560)
+  constexpr int UN = 4;                       // keys per inner iteration
+  extern __shared__ __align__(16) float att_smem[];
+  float* Ks = att_smem;                                       // [nk][4]
+  float* Vs = Ks + (size_t)nk * 4;                            // [nk][4]
+  float* Part = Vs + (size_t)nk * 4;                          // [ATB_WARPS][ATT_ROWS][D + 2]: acc, m, l per key slice
+  float* Qs = Part + ATB_WARPS * ATT_ROWS * (D + 2);          // [ATT_ROWS][D]
+  float* Ps = Qs + ATT_ROWS * D;                              // [ATT_ROWS][nk_pad], pre-scaled by log2(e)
+  const int h = blockIdx.y;
+  const int HD = heads * D;
+  const int row0 = blockIdx.x * ATT_ROWS;
+  const int b_begin = blockIdx.z * b_per_cta, b_end = min(B, b_begin + b_per_cta);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int r = warp; r < ATT_ROWS; r += ATB_WARPS) {
+    const int i = min(row0 + r, nq - 1);
+    const float* prow = pos ? pos + ((long long)h * nq + i) * nk : nullptr;
+    for (int j = lane; j < nk; j += 32) Ps[r * nk_pad + j] = prow ? __ldg(prow + j) * LOG2E : 0.f;
+  }
+  float4 kreg[PF], vreg[PF], qreg = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int b) {
+    const long long kv0 = KVHM ? ((long long)b * heads + h) * nk * D : (long long)b * nk * HD + h * D;
+    const int kvs = KVHM ? D : HD;                           // floats between consecutive keys of this (sample, head)
+    const float* kb = k + kv0;
+    const float* vb = v + kv0;
+    if (tid < ATT_ROWS) {
+      const int i = min(row0 + tid, nq - 1);              // rows past the end recompute the last row (not stored)
+      qreg = __ldg(reinterpret_cast<const float4*>(q + ((long long)b * nq + i) * HD + h * D));
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int j = tid + u * ATB_THREADS;
+      if (j < nk) {
+        kreg[u] = __ldg(reinterpret_cast<const float4*>(kb + (long long)j * kvs));
+        vreg[u] = __ldg(reinterpret_cast<const float4*>(vb + (long long)j * kvs));
+      }
+    }
+  };
+  if (b_begin < b_end) prefetch(b_begin);
+  const float sc = inv_scale * LOG2E;
+  // this warp's key slice (multiples of UN except the last one)
+  const int per = ((nk + ATB_WARPS - 1) / ATB_WARPS + UN - 1) / UN * UN;
+  const int j0 = min(warp * per, nk), j1 = min(j0 + per, nk);
+  const float* prow = Ps + (size_t)lane * nk_pad;
+
+  for (int b = b_begin; b < b_end; ++b) {
+    __syncthreads();                          // previous sample: K / V consumed, partials merged
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int j = tid + u * ATB_THREADS;
+      if (j < nk) {
+        *reinterpret_cast<float4*>(Ks + j * 4) = kreg[u];
+        *reinterpret_cast<float4*>(Vs + j * 4) = vreg[u];
+      }
+    }
+    if (tid < ATT_ROWS) *reinterpret_cast<float4*>(Qs + tid * 4) = qreg;
+    __syncthreads();
+    if (b + 1 < b_end) prefetch(b + 1);
+
+    const float4 q4 = *reinterpret_cast<const float4*>(Qs + lane * 4);
+    const float q0 = q4.x * sc, q1 = q4.y * sc, q2 = q4.z * sc, q3 = q4.w * sc;
+    float m = -INFINITY, mt = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // lazy rescale: the reference point m only moves when a score exceeds it by 2^LAZY; the test is a warp vote
+    // so that the rescale stays a real, rarely taken branch
+    auto bump = [&](float smax) {
+      if (__any_sync(0xffffffffu, smax > mt)) {
+        if (smax > mt) {
+          const float corr = (m == -INFINITY) ? 0.f : ex2_approx(m - smax);
+          l *= corr; a0 *= corr; a1 *= corr; a2 *= corr; a3 *= corr;
+          m = smax;
+          mt = smax + LAZY;
+        }
+      }
+    };
+    int j = j0;
+    for (; j + UN <= j1; j += UN) {
+      float4 kk[UN], vv[UN];
+      float s[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        kk[u] = *reinterpret_cast<const float4*>(Ks + (j + u) * 4);
+        vv[u] = *reinterpret_cast<const float4*>(Vs + (j + u) * 4);
+        s[u] = prow[j + u];
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        s[u] = fmaf(q3, kk[u].w, fmaf(q2, kk[u].z, fmaf(q1, kk[u].y, fmaf(q0, kk[u].x, s[u]))));
+      bump(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])));
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const float e = ex2_approx(s[u] - m);
+        l += e;
+        a0 = fmaf(e, vv[u].x, a0); a1 = fmaf(e, vv[u].y, a1); a2 = fmaf(e, vv[u].z, a2); a3 = fmaf(e, vv[u].w, a3);
+      }
+    }
+    for (; j < j1; ++j) {                     // ragged tail of the last slice
+      const float4 kk = *reinterpret_cast<const float4*>(Ks + j * 4);
+      const float4 vv = *reinterpret_cast<const float4*>(Vs + j * 4);
+      const float s1 = fmaf(q3, kk.w, fmaf(q2, kk.z, fmaf(q1, kk.y, fmaf(q0, kk.x, prow[j]))));
+      bump(s1);
+      const float e = ex2_approx(s1 - m);
+      l += e;
+      a0 = fmaf(e, vv.x, a0); a1 = fmaf(e, vv.y, a1); a2 = fmaf(e, vv.z, a2); a3 = fmaf(e, vv.w, a3);
+    }
+    float* pr = Part + ((size_t)warp * ATT_ROWS + lane) * (D + 2);
+    pr[0] = a0; pr[1] = a1; pr[2] = a2; pr[3] = a3; pr[4] = m; pr[5] = l;
+    __syncthreads();
+    // merge the 16 key slices: one thread per (row, channel)
+    if (tid < ATT_ROWS * D) {
+      const int r = tid / D, c = tid % D;
+      if (row0 + r < nq) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int s2 = 0; s2 < ATB_WARPS; ++s2) M = fmaxf(M, Part[((size_t)s2 * ATT_ROWS + r) * (D + 2) + D]);
+        float L = 0.f, a = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < ATB_WARPS; ++s2) {
+          const float* p2 = Part + ((size_t)s2 * ATT_ROWS + r) * (D + 2);
+          const float f = p2[D] == -INFINITY ? 0.f : ex2_approx(p2[D] - M);
+          L = fmaf(p2[D + 1], f, L);
+          a = fmaf(p2[c], f, a);
+        }
+        out[((long long)b * nq + row0 + r) * HD + h * D + c] = a / L;
+      }
+    }
+  }
+}
+
 // Backward of the same core.  One warp per query row; recomputes the softmax statistics,
 // then ds_j = p_j (dp_j - delta) with delta = gout_i . out_i.
 //   gq_i = inv_scale * sum_j ds_j k_j          (registers + warp reduce)
@@ -366,9 +513,19 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
   }
 }
 
+// the batch-looping kernels serve LARGE pos_embed blocks (level 0: 44.8 MB re-read per sample otherwise)
+static bool big_pos_case(const float* pos, int B, int heads, int nq, int nk) {
+  return pos != nullptr && (size_t)heads * nq * nk * sizeof(float) > (16u << 20) && B >= 4;
+}
+static size_t rows_kernel_smem(int nk, int D) {
+  const int nk_pad = nk + ((33 - (nk & 31)) & 31);
+  return sizeof(float) * (2 * (size_t)nk * 4 + (size_t)ATB_WARPS * ATT_ROWS * (D + 2) + (size_t)ATT_ROWS * D +
+                          (size_t)ATT_ROWS * nk_pad);
+}
+
 template <int D>
 static int launch_fwd(const float* q, const float* k, const float* v, const float* pos, float* out,
-                      int B, int heads, int nq, int nk, float inv_scale, cudaStream_t st) {
+                      int B, int heads, int nq, int nk, float inv_scale, cudaStream_t st, bool kvhm = false) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   // batch-looping kernel for LARGE pos_embed blocks (level 0: 44.8 MB re-read per sample otherwise):
@@ -378,9 +535,26 @@ static int launch_fwd(const float* q, const float* k, const float* v, const floa
   const int nk_pad = nk + ((33 - (nk & 31)) & 31);           // row stride = 1 mod 32: the RW rows of a pass hit distinct banks
   const size_t smem_b = sizeof(float) * (2 * (size_t)nk * KPad<D>::stride + (size_t)KSv * ATT_ROWS * (D + 2) +
                                          (size_t)ATT_ROWS * D + (size_t)ATT_ROWS * nk_pad);
-  const bool big_pos = pos != nullptr && (size_t)heads * nq * nk * sizeof(float) > (16u << 20) && B >= 4;
+  const bool big_pos = big_pos_case(pos, B, heads, nq, nk);
   if (big_pos && smem_b <= 226 * 1024 && (long long)nk * (D / 4) <= 2560) {
     const int blocks_xy = cdiv(nq, ATT_ROWS) * heads;
+    if constexpr (D == 4) {
+      // lanes-as-rows variant (see attn_fwd_rows_kernel); SGTA_ATTN_KEYS=1 in the environment keeps the lanes-as-keys one
+      static const bool keys_variant = getenv("SGTA_ATTN_KEYS") != nullptr;
+      const size_t smem_r = rows_kernel_smem(nk, D);
+      if ((!keys_variant || kvhm) && smem_r <= 226 * 1024) {
+        int zc = cdiv(2 * sms, blocks_xy);
+        if (zc > B) zc = B;
+        if (zc < 1) zc = 1;
+        const int bpc = cdiv(B, zc);
+        zc = cdiv(B, bpc);
+        auto kern = kvhm ? attn_fwd_rows_kernel<D, true> : attn_fwd_rows_kernel<D, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+        kern<<<dim3(cdiv(nq, ATT_ROWS), heads, zc), ATB_THREADS, smem_r, st>>>(q, k, v, pos, out, B, heads, nq, nk, nk_pad,
+                                                                             bpc, inv_scale);
+        return check_launch("attn_fwd_rows_kernel");
+      }
+    }
     int zchunks = cdiv(2 * sms, blocks_xy);                    // >= 2 CTAs per SM worth of parallelism when B allows
     if (zchunks > B) zchunks = B;
     if (zchunks < 1) zchunks = 1;
@@ -421,6 +595,20 @@ static int launch_bwd(const float* q, const float* k, const float* v, const floa
 }  // namespace sgta
 
 using namespace sgta;
+
+extern "C" int sgta_attn_kvhm_supported(int B, int heads, int nq, int nk, int d, int has_pos) {
+  return d == 4 && has_pos && B >= 4 && (size_t)heads * nq * nk * sizeof(float) > (16u << 20) && nk <= 2560 &&
+         rows_kernel_smem(nk, 4) <= 226 * 1024;
+}
+
+extern "C" int sgta_attn_forward_kvhm(const void* q, const void* k_hm, const void* v_hm, const void* pos, void* out,
+                                      int B, int heads, int nq, int nk, int d, float inv_scale, void* stream) {
+  SGTA_REQUIRE(q && k_hm && v_hm && pos && out, "sgta_attn_forward_kvhm: null pointer");
+  SGTA_REQUIRE(sgta_attn_kvhm_supported(B, heads, nq, nk, d, 1),
+               "sgta_attn_forward_kvhm: shape not served by the head-major kernel (see sgta_attn_kvhm_supported)");
+  return launch_fwd<4>((const float*)q, (const float*)k_hm, (const float*)v_hm, (const float*)pos, (float*)out, B, heads,
+                       nq, nk, inv_scale, (cudaStream_t)stream, true);
+}
 
 extern "C" int sgta_attn_forward(const void* q, const void* k, const void* v, const void* pos,
                                  void* out, int B, int heads, int nq, int nk, int d,

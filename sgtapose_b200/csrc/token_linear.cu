@@ -15,6 +15,7 @@ struct TokenLinearP {
   const float *x1, *x2, *w, *bias;
   float* y;
   int M, N, K1, K2, relu;
+  int hm_heads, hm_n;      // hm_heads > 0: rows are (b, j) with j < hm_n, columns (h, d): store y as [B, heads, hm_n, N / heads]
 };
 
 template <int BM, int BN>
@@ -88,9 +89,16 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) token_linear_kernel(const
     if (m >= p.M) break;
     float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
     if (p.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-    *reinterpret_cast<float4*>(p.y + (size_t)m * p.N + n) = o;
+    size_t dst = (size_t)m * p.N + n;
+    if (p.hm_heads > 0) {
+      const int D = p.N / p.hm_heads, b = m / p.hm_n, j = m - b * p.hm_n, h = n / D;
+      dst = (((size_t)b * p.hm_heads + h) * p.hm_n + j) * D + (n - h * D);
+    }
+    *reinterpret_cast<float4*>(p.y + dst) = o;
   }
 }
+
+int launch_token_linear(TokenLinearP& p, cudaStream_t st);
 
 }  // namespace sgta
 
@@ -101,8 +109,24 @@ extern "C" int sgta_token_linear(const void* x1, int K1, const void* x2, int K2,
   SGTA_REQUIRE(x1 && w && y, "sgta_token_linear: null pointer");
   SGTA_REQUIRE(M > 0 && N > 0 && N % 4 == 0 && K1 > 0 && K1 % 16 == 0 && K2 >= 0 && K2 % 16 == 0 && (K2 == 0 || x2),
                "sgta_token_linear: M > 0, N %% 4 == 0, K1 and K2 multiples of 16 (x2 required when K2 > 0)");
-  TokenLinearP p{(const float*)x1, (const float*)x2, (const float*)w, (const float*)bias, (float*)y, M, N, K1, K2, relu};
-  cudaStream_t st = (cudaStream_t)stream;
+  TokenLinearP p{(const float*)x1, (const float*)x2, (const float*)w, (const float*)bias, (float*)y, M, N, K1, K2, relu, 0, 0};
+  return launch_token_linear(p, (cudaStream_t)stream);
+}
+
+// The K / V projections with a HEAD-MAJOR result: x [B*n_tokens, K], w [N, K] -> y [B, heads, n_tokens, N / heads]
+// (what sgta_attn_forward_kvhm reads: the slab of one (sample, head) is contiguous).
+extern "C" int sgta_token_linear_heads(const void* x, int K, const void* w, void* y, int M, int N, int n_tokens, int heads,
+                                       void* stream) {
+  SGTA_REQUIRE(x && w && y, "sgta_token_linear_heads: null pointer");
+  SGTA_REQUIRE(M > 0 && N > 0 && K > 0 && K % 16 == 0 && heads > 0 && N % heads == 0 && (N / heads) % 4 == 0 &&
+               n_tokens > 0 && M % n_tokens == 0, "sgta_token_linear_heads: bad shape");
+  TokenLinearP p{(const float*)x, nullptr, (const float*)w, nullptr, (float*)y, M, N, K, 0, 0, heads, n_tokens};
+  return launch_token_linear(p, (cudaStream_t)stream);
+}
+
+namespace sgta {
+int launch_token_linear(TokenLinearP& p, cudaStream_t st) {
+  const int M = p.M, N = p.N;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   if ((long long)cdiv(M, 64) * cdiv(N, 64) >= sms) {
@@ -112,3 +136,4 @@ extern "C" int sgta_token_linear(const void* x1, int K1, const void* x2, int K2,
   }
   return check_launch("token_linear_kernel");
 }
+}  // namespace sgta

@@ -258,14 +258,19 @@ class InferenceEngine:
             p = "transformer.%d.layers.0" % i
             a = p + ".cross_attn"
             heads = 8
-            Kp = fusion.token_linear(pre_key, sd[a + ".w_k.weight"])   # K, V are shared by the 3 layers
-            Vp = fusion.token_linear(pre_key, sd[a + ".w_v.weight"])
-            scale = (Kp.shape[-1] // heads) ** 0.5
+            hid = sd[a + ".w_k.weight"].shape[0]
+            n_tok = pre_key.shape[1]
             pos = sd[a + ".pos_embed"] if self.use_pos else None
+            # level 0 at large batch: K / V head-major, so that the batch-looping kernel prefetches contiguous slabs
+            hm = fusion.kv_head_major_supported(B, heads, n_tok, n_tok, hid // heads, pos is not None)
+            proj = (lambda w: fusion.token_linear_heads(pre_key, w, heads)) if hm else (lambda w: fusion.token_linear(pre_key, w))
+            Kp = proj(sd[a + ".w_k.weight"])                          # K, V are shared by the 3 layers
+            Vp = proj(sd[a + ".w_v.weight"])
+            scale = (hid // heads) ** 0.5
             q = cur_q
             qp = fusion.token_linear(q, sd[a + ".w_q.weight"])
             for layer in range(3):                                    # one shared layer (dla.py:788-789)
-                att = fusion.attention_core(qp, Kp, Vp, pos, heads, scale)
+                att = (fusion.attention_core_kvhm if hm else fusion.attention_core)(qp, Kp, Vp, pos, heads, scale)
                 # fc + residual + LN1 + FFN + residual + LN3 (+ the next layer's w_q) in one launch
                 q, qp = fusion.token_mlp(att, q, self._tr(a + ".fc.weight"), sd[a + ".fc.bias"],
                                          sd[p + ".norm1.weight"], sd[p + ".norm1.bias"],

@@ -191,6 +191,33 @@ def token_linear(x, w, bias=None, x2=None, relu=False):
     return y
 
 
+def kv_head_major_supported(B, heads, nq, nk, d, has_pos=True):
+    """Does the head-major K/V form of the attention core serve this shape (level 0 at the bench batch)?"""
+    return bool(_lib.load().sgta_attn_kvhm_supported(B, heads, nq, nk, d, int(bool(has_pos))))
+
+
+def token_linear_heads(x, w, heads):
+    """w_k / w_v projection with a head-major result: x [B,n,K], w [N,K] -> [B, heads, n, N/heads] (inference only)."""
+    x = x.contiguous()
+    B, n, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(B, heads, n, N // heads, device=x.device, dtype=torch.float32)
+    _lib.call("sgta_token_linear_heads", _lib.ptr(x), K, _lib.ptr(w), _lib.ptr(y), B * n, N, n, heads, _lib.stream())
+    return y
+
+
+def attention_core_kvhm(q, k_hm, v_hm, pos, heads, scale):
+    """attention_core with head-major K / V ([B, heads, nk, d], `token_linear_heads`); q and the result stay
+    "b n (h d)".  Inference only; shapes as accepted by `kv_head_major_supported`."""
+    q = q.contiguous()
+    B, nq, HD = q.shape
+    nk, d = k_hm.shape[2], k_hm.shape[3]
+    out = torch.empty_like(q)
+    _lib.call("sgta_attn_forward_kvhm", _lib.ptr(q), _lib.ptr(k_hm), _lib.ptr(v_hm), _lib.ptr(pos.contiguous()),
+              _lib.ptr(out), B, heads, nq, nk, d, float(1.0 / scale), _lib.stream())
+    return out
+
+
 def token_mlp(att, q, fc_wt, fc_b, ln1_w, ln1_b, w1, b1, w2t, b2, ln3_w, ln3_b, wq_next=None, eps=1e-5):
     """Post-attention half of TransformerEncoderLayer.forward (dla.py:734-743) in ONE launch:
     q2 = LN3(q1 + FFN(q1)), q1 = LN1(fc(att) + q); also the next layer's query projection w_q q2 when

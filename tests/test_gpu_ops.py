@@ -149,6 +149,34 @@ def test_attention_core_vs_torch(n, d, B):
     assert rel_err(out2, ref2) < 1e-4
 
 
+def test_attention_head_major_kv_vs_torch():
+    """Level-0 form the engine runs at the bench batch: w_k / w_v written head-major by token_linear_heads, the
+    lanes-as-rows batch-looping attention kernel reading contiguous (sample, head) slabs; vs fp64 torch (dla.py:868-885)."""
+    import torch.nn.functional as F
+    from sgtapose_b200 import fusion
+    n, d, B, heads = 1183, 4, 5, 8
+    assert fusion.kv_head_major_supported(B, heads, n, n, d) and not fusion.kv_head_major_supported(2, heads, n, n, d)
+    assert not fusion.kv_head_major_supported(B, heads, 343, 343, 8)
+    x, qx = C.gen(1, B, n, 16), C.gen(2, B, n, heads * d)
+    wk, wv = C.gen(3, heads * d, 16) * 0.4, C.gen(4, heads * d, 16) * 0.4
+    pos = C.gen(5, heads, n, n) * 0.5
+    scale = d ** 0.5
+    D = lambda t: t.double()
+    K, V = F.linear(D(x), D(wk)), F.linear(D(x), D(wv))
+    split = lambda t: t.reshape(B, n, heads, d).permute(0, 2, 1, 3)
+    e = split(D(qx)) @ split(K).transpose(-1, -2) / scale + D(pos)
+    ref = (torch.softmax(e, -1) @ split(V)).permute(0, 2, 1, 3).reshape(B, n, heads * d)
+    k_hm = fusion.token_linear_heads(x.to(DEV), wk.to(DEV), heads)
+    v_hm = fusion.token_linear_heads(x.to(DEV), wv.to(DEV), heads)
+    assert rel_err(k_hm.cpu(), split(K).float()) < 5e-6
+    out = fusion.attention_core_kvhm(qx.to(DEV), k_hm, v_hm, pos.to(DEV), heads, scale).cpu()
+    assert rel_err(out, ref.float()) < 1e-4
+    # same numbers as the "b n (h d)" form of the same kernel
+    std = fusion.attention_core(qx.to(DEV), fusion.token_linear(x.to(DEV), wk.to(DEV)), fusion.token_linear(x.to(DEV), wv.to(DEV)),
+                                pos.to(DEV), heads, scale).cpu()
+    assert torch.equal(out, std)
+
+
 @pytest.mark.parametrize("C,n,B", [(16, 1183, 3), (32, 343, 2), (64, 63, 5)])
 def test_token_mlp_vs_torch(C, n, B):
     """Fused fc + LN1 + FFN + LN3 (+ next w_q) vs the same torch ops in fp64 (dla.py:728-743, :886-887)."""

@@ -36,6 +36,27 @@ def test_planes_roundtrip(ns, shape):
         assert (back - x).abs().max().item() <= 3e-7 * x.abs().max().item()
 
 
+def test_planes_fp32_mode_saturates_at_fp16_range():
+    """fp32 mode stores hi = fp16(v): |v| beyond 65504 saturates (csrc/planes.cuh clamp_h) instead of turning into
+    inf -- stated in include/sgta_b200.h.  Values up to the limit keep ~2^-22 relative accuracy; a convolution whose
+    OUTPUT exceeds the range is clamped in its epilogue, one whose inputs sit at 6e4 still sums exactly in fp32."""
+    from sgtapose_b200 import planes as P
+    x = torch.zeros(1, 64, 4, 4)
+    x[0, 0, 0, 0], x[0, 1, 0, 0], x[0, 2, 0, 0], x[0, 3, 0, 0] = 65504.0, 7e4, -1e6, 60000.123
+    back = _buf(x, 2).to_nchw().cpu()
+    assert back[0, 0, 0, 0] == 65504.0 and back[0, 1, 0, 0] == 65504.0 and back[0, 2, 0, 0] == -65504.0
+    assert abs(back[0, 3, 0, 0].item() - 60000.123) < 60000 * 3e-7
+    xb = _buf(torch.full((1, 64, 6, 6), 6.0e4), 2)
+    w = torch.zeros(64, 64, 1, 1)
+    w[0, :2] = 1.0                    # output 1.2e5 -> clamped
+    w[1, 0], w[1, 1] = 1.0, -0.5      # output 3.0e4 -> exact
+    spec = P.ConvSpec(P.weight_matrix(w.to(DEV)), torch.ones(64, device=DEV), torch.zeros(64, device=DEV), 64, 1, 1, 2)
+    yb = P.PlaneBuf(1, 64, 6, 6, 2, DEV)
+    P.conv(spec, xb.full, yb.full)
+    y = yb.to_nchw().cpu()
+    assert torch.all(y[0, 0] == 65504.0) and torch.all(y[0, 1] == 3.0e4) and torch.all(y[0, 2] == 0.0)
+
+
 SHIFT_CFGS = [  # B, Cin, Cout, H, W, k
     (2, 64, 64, 24, 24, 3),
     (1, 64, 64, 13, 17, 3),
