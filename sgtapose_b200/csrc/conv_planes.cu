@@ -47,7 +47,12 @@ template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("se
 constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
                                                          // each, tests/cuda/tma_bw_probe.cu): spread them over 4
 constexpr int S_EPI_NH = 2;                              // epilogue warps per TMEM lane quadrant (each takes half the columns)
-constexpr int S_THREADS = (S_TMA_WARPS + 1 + 4 * S_EPI_NH) * 32;    // TMA warps, MMA, epilogue warps
+// warps: [4 TMA | MMA issuer, 3 idle | 4 * S_EPI_NH epilogue] -- whole warpgroups, so fp32 mode can hand the registers
+// of the first two groups to the epilogue warps (setmaxnreg): at 128 registers the band-drain epilogue spilled
+constexpr int S_W_MMA = S_TMA_WARPS, S_W_EPI = 8;
+constexpr int S_THREADS = (S_W_EPI + 4 * S_EPI_NH) * 32;
+// per-tile staging of the epilogue's scale / shift rows in shared memory: 2 buffers x [scale | shift] x 128 columns
+constexpr int EPI_SS_BYTES = 2 * 2 * 128 * 4;
 constexpr int S_MAX_SB = 24;                             // B ring slots (resident weights: one per K block)
 
 enum { PROD_DCN = 0, PROD_STRIDE = 1, PROD_SMALLC = 2 };
@@ -70,6 +75,8 @@ struct ConvP {
   int acc_r;             // D0 accumulators per stage (k steps rotate over them: shorter fp32 chains)
   int acc_stages;        // TMEM accumulator stages (2 = epilogue overlaps the next tile)
   int nslots, nd1;       // fp32 mode: D0 band slots (2..6) and D1 buffers (1..2) in TMEM, NT columns each
+  int wide;              // fp32 mode: band slots are [D0 | D1] (2 NT columns) filled by A_hi x [B_hi | B_lo] + A_lo x B_hi
+  int slot_cols;         // TMEM columns per band slot: NT, or 2 NT when wide
   int stride;
   int spk;               // shift kernel: super-pixel weights, zero K steps of the neighbour taps skipped (EPI_SP2SC)
   int sx;                // gather kernels: column stride of the input anchor (== stride, except the super-pixel stem: 4)
@@ -222,6 +229,47 @@ __device__ __forceinline__ void issue_band_f32(uint32_t a_base, uint32_t a_plane
   mma_commit(a_rel);
 }
 
+// ---- fp32 mode, wide form: two MMAs per K step instead of three.  The hi and lo planes of a weight tile lie back to
+// back in shared memory (NT rows of 128 B each, same swizzle phase), so ONE MMA of N = 2 NT columns computes
+// A_hi x [B_hi | B_lo] into a band slot [D0 | D1] and a second one of N = NT adds A_lo x B_hi to the D1 half: A_hi is
+// fetched from shared memory once instead of twice (operand bytes per K step: 24 -> 20 KB at NT = 128, 18 -> 14 KB at
+// 64, 15 -> 11 KB at 32 -- the SS-mode operand fetch is what bounds these kernels), and the issuing thread has a
+// third fewer instructions.  D1 is drained with its band (the epilogue adds d0 + d1 * 2^-11), so there is no
+// tile-long D1 buffer and no D1 hand-shake.
+template <int KMASK = 15>
+__device__ __forceinline__ void issue_kblock_f32w(uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t tS, uint32_t NT,
+                                                  uint32_t idesc_w, uint32_t idesc_n, uint32_t acc0) {
+  const uint64_t ah = smem_desc_sw128(a_addr), bh = smem_desc_sw128(b_addr);
+  const uint64_t al = smem_desc_sw128(a_addr + a_plane);
+  constexpr int K0 = (KMASK & 1) ? 0 : (KMASK & 2) ? 1 : (KMASK & 4) ? 2 : 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!((KMASK >> k) & 1)) continue;
+    mma_bf16_ss(tS, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc_w, k == K0 ? acc0 : 1u);
+    mma_bf16_ss(tS + NT, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc_n, 1u);
+  }
+}
+template <int TAPS, int SPK = 0>
+__device__ __forceinline__ void issue_band_f32w(uint32_t a_base, uint32_t a_plane, const uint32_t (&b_addr)[3], uint32_t tS,
+                                                uint32_t NT, uint32_t idesc_w, uint32_t idesc_n, uint32_t acc0,
+                                                uint64_t* const (&b_rel)[3], uint64_t* a_rel) {
+  if constexpr (SPK && TAPS == 3) {
+    issue_kblock_f32w<15>(a_base + 128u, a_plane, b_addr[1], tS, NT, idesc_w, idesc_n, acc0);     // centre tap first
+    mma_commit(b_rel[1]);
+    issue_kblock_f32w<8>(a_base, a_plane, b_addr[0], tS, NT, idesc_w, idesc_n, 1u);
+    mma_commit(b_rel[0]);
+    issue_kblock_f32w<1>(a_base + 256u, a_plane, b_addr[2], tS, NT, idesc_w, idesc_n, 1u);
+    mma_commit(b_rel[2]);
+  } else {
+#pragma unroll
+    for (int dx = 0; dx < TAPS; ++dx) {
+      issue_kblock_f32w(a_base + (uint32_t)dx * 128u, a_plane, b_addr[dx], tS, NT, idesc_w, idesc_n, dx == 0 ? acc0 : 1u);
+      mma_commit(b_rel[dx]);
+    }
+  }
+  mma_commit(a_rel);
+}
+
 // explicit shared-memory accesses (pointers derived from the dynamic smem base otherwise compile to
 // generic LD / ST)
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -324,8 +372,9 @@ __device__ __forceinline__ void stem_pixel(const ConvP& p, const float (&fa)[16]
 }
 
 // scale / shift / residual / activation / store of 16 columns held in registers
-template <int NS>
-__device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int n, float (&o)[16]) {
+// SS: scale[16] at shared-memory address ss, shift[16] at ss + 512 (staged by fp32_epilogue_loop)
+template <int NS, bool SS = false>
+__device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int n, float (&o)[16], uint32_t ss = 0u) {
   uint4 rv[2][NS];
   if (e.has_res) {
 #pragma unroll
@@ -338,8 +387,15 @@ __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int 
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale + n) + j);
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + n) + j);
+    float4 a, b4;
+    if constexpr (SS) {
+      const uint4 ua = lds128(ss + 16u * j), ub = lds128(ss + 512u + 16u * j);
+      a = make_float4(__uint_as_float(ua.x), __uint_as_float(ua.y), __uint_as_float(ua.z), __uint_as_float(ua.w));
+      b4 = make_float4(__uint_as_float(ub.x), __uint_as_float(ub.y), __uint_as_float(ub.z), __uint_as_float(ub.w));
+    } else {
+      a = __ldg(reinterpret_cast<const float4*>(p.scale + n) + j);
+      b4 = __ldg(reinterpret_cast<const float4*>(p.shift + n) + j);
+    }
     o[4 * j] = fmaf(o[4 * j], a.x, b4.x); o[4 * j + 1] = fmaf(o[4 * j + 1], a.y, b4.y);
     o[4 * j + 2] = fmaf(o[4 * j + 2], a.z, b4.z); o[4 * j + 3] = fmaf(o[4 * j + 3], a.w, b4.w);
   }
@@ -422,12 +478,31 @@ __device__ __forceinline__ void epi_row_setup(const ConvP& p, int m, EpiRow& e) 
 }
 template <int NG, int NH, bool BACKOFF>
 __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem, int total, int nbands, int q, int half,
-                                                   int lane, uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty) {
+                                                   int lane, uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty,
+                                                   float* epi_ss) {
   const int NT = p.NT, g0 = half * NG;
+  const bool wide = p.wide != 0;
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
   Ring rs{0u, 0u, p.nslots}, rd{0u, 0u, p.nd1};
+  // scale / shift of the N tile staged in shared memory by the epilogue warps themselves (one element per thread, two
+  // buffers): read per 16-column group from global memory at the end of a tile they were L1 misses under the TMA
+  // traffic -- half of the epilogue warps' stall samples on the 64 -> 768 head convolution
+  const bool stage_ss = p.epi != SGTA_EPI_STEM && p.epi != SGTA_EPI_STEM_SP;
+  int ss_nt = -1;
+  uint32_t ss_buf = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+    if (stage_ss && nt != ss_nt) {
+      ss_nt = nt;
+      ss_buf ^= 1u;
+      const int et = (half * 4 + q) * 32 + lane;
+      if (et < NT) {
+        epi_ss[ss_buf * 256 + et] = __ldg(p.scale + nt * NT + et);
+        epi_ss[ss_buf * 256 + 128 + et] = __ldg(p.shift + nt * NT + et);
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(NH * 128) : "memory");
+    }
+    const uint32_t ss = smem_u32(epi_ss) + ss_buf * 1024u;
     float acc[NG][16];
 #pragma unroll
     for (int g = 0; g < NG; ++g)
@@ -438,15 +513,41 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
       else mbar_wait(&slot_full[rs.i], rs.ph);
       tc_fence_after();
       if (!(p.dbg & 4)) {
-        const uint32_t ts = lane_base + rs.i * (uint32_t)NT;
+        const uint32_t ts = lane_base + rs.i * (uint32_t)p.slot_cols;
+        if (wide) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if ((g0 + g) * 16 < NT) {
-            uint32_t d[16];
-            tmem_ld16(ts + (uint32_t)((g0 + g) * 16), d);
-            tmem_ld_wait();
+          for (int g = 0; g < NG; ++g) {
+            if ((g0 + g) * 16 < NT) {
+              if constexpr (NG <= 4) {
+                uint32_t d[16], e1[16];
+                tmem_ld16(ts + (uint32_t)((g0 + g) * 16), d);
+                tmem_ld16(ts + (uint32_t)(NT + (g0 + g) * 16), e1);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[g][j] += __uint_as_float(d[j]);
+                for (int j = 0; j < 16; ++j) acc[g][j] += fmaf(__uint_as_float(e1[j]), LO_INV, __uint_as_float(d[j]));
+              } else {                                     // 128 accumulators per thread: one 16-register buffer
+                uint32_t d[16];
+                tmem_ld16(ts + (uint32_t)((g0 + g) * 16), d);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[g][j] += __uint_as_float(d[j]);
+                tmem_ld16(ts + (uint32_t)(NT + (g0 + g) * 16), d);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[g][j] = fmaf(__uint_as_float(d[j]), LO_INV, acc[g][j]);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if ((g0 + g) * 16 < NT) {
+              uint32_t d[16];
+              tmem_ld16(ts + (uint32_t)((g0 + g) * 16), d);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[g][j] += __uint_as_float(d[j]);
+            }
           }
         }
       }
@@ -455,23 +556,25 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
       if (lane == 0) mbar_arrive(&slot_empty[rs.i]);
       rs.next();
     }
-    if (!(p.dbg & 4)) {
-      const uint32_t td = lane_base + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+    if (!wide) {
+      if (!(p.dbg & 4)) {
+        const uint32_t td = lane_base + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        if ((g0 + g) * 16 < NT) {
-          uint32_t d[16];
-          tmem_ld16(td + (uint32_t)((g0 + g) * 16), d);
-          tmem_ld_wait();
+        for (int g = 0; g < NG; ++g) {
+          if ((g0 + g) * 16 < NT) {
+            uint32_t d[16];
+            tmem_ld16(td + (uint32_t)((g0 + g) * 16), d);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[g][j] = fmaf(__uint_as_float(d[j]), LO_INV, acc[g][j]);
+            for (int j = 0; j < 16; ++j) acc[g][j] = fmaf(__uint_as_float(d[j]), LO_INV, acc[g][j]);
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d1_empty[rd.i]);
+      rd.next();
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&d1_empty[rd.i]);
-    rd.next();
     if (p.dbg & (4 | 8192)) continue;                       // 8192: drain TMEM but skip the math and the stores
     EpiRow e;
     epi_row_setup(p, p.tile2d ? tile_row_m(p, t / p.n_tiles, q * 32 + lane) : m0 + q * 32 + lane, e);
@@ -498,17 +601,17 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
     }
 #pragma unroll
     for (int g = 0; g < NG; ++g)
-      if ((g0 + g) * 16 < NT) epi_finish<2>(p, e, nt * NT + (g0 + g) * 16, acc[g]);
+      if ((g0 + g) * 16 < NT) epi_finish<2, true>(p, e, nt * NT + (g0 + g) * 16, acc[g], ss + (uint32_t)((g0 + g) * 64));
   }
 }
 template <int NH, bool BACKOFF, int MAXNG = 8 / NH>
 __device__ __forceinline__ void fp32_epilogue(const ConvP& p, uint32_t tmem, int total, int nbands, int q, int half, int lane,
-                                              uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty) {
+                                              uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty, float* epi_ss) {
   const int per = ((p.NT + 15) / 16 + NH - 1) / NH;          // 16-column groups per thread (the launcher keeps it <= MAXNG)
-  if (per <= 1) fp32_epilogue_loop<1, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
-  else if (per <= 2) fp32_epilogue_loop<2, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
-  else if (per <= 4 || MAXNG <= 4) fp32_epilogue_loop<4, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
-  else if constexpr (MAXNG > 4) fp32_epilogue_loop<8, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty);
+  if (per <= 1) fp32_epilogue_loop<1, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty, epi_ss);
+  else if (per <= 2) fp32_epilogue_loop<2, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty, epi_ss);
+  else if (per <= 4 || MAXNG <= 4) fp32_epilogue_loop<4, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty, epi_ss);
+  else if constexpr (MAXNG > 4) fp32_epilogue_loop<8, NH, BACKOFF>(p, tmem, total, nbands, q, half, lane, slot_full, slot_empty, d1_empty, epi_ss);
 }
 
 // NH epilogue warps per lane quadrant; `half` in [0, NH) is this warp's share
@@ -618,6 +721,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   uint64_t *acc_full = bars + 32, *acc_empty = bars + 34;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
   uint64_t *slot_full = bars + 38, *slot_empty = bars + 44;     // fp32 mode: up to 6 D0 band slots (acc_empty = D1 buffers)
+  float* epi_ss = reinterpret_cast<float*>(bars + 128);         // scale / shift staging of the fp32 epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -627,7 +731,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     for (int s = 0; s < 6; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 4 * S_EPI_NH); }
     fence_mbar_init();
   }
-  if (warp == S_TMA_WARPS) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  if (warp == S_W_MMA) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -635,10 +739,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   const uint32_t acc_stride = (uint32_t)((p.acc_r + NS - 1) * NT);
   const int total = p.m_tiles * p.n_tiles;
   const int Wp = p.x.W + 2;
+
   const int nb = p.taps == 9 ? 3 : 1;
   const int ntap_b = p.taps == 9 ? 3 : 1;
 
   if (warp < S_TMA_WARPS) {
+    if constexpr (NS == 2) reg_dec<40>();
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producers
       // every copy (one plane of an A band, one B tile) belongs to a FIXED warp per ring slot, so the
@@ -683,10 +789,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == S_TMA_WARPS) {
+  } else if (warp == S_W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (whole warp
     // walks the loop and waits; one elected lane issues, so operands stay in uniform registers)
+    if constexpr (NS == 2) reg_dec<40>();
     const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+    const uint32_t idesc_w = idesc_f16_f32(TM, 2 * NT);
     int st = 0, sb = 0;
     uint32_t aph = 0, bph = 0;             // parity to wait for on the *_full barriers
     uint32_t as = 0, accph = 1;            // accumulator stage and parity of its acc_empty barrier
@@ -696,9 +804,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
       const int m0 = (t / p.n_tiles) * TM;
       uint32_t tacc = 0, tD0 = 0, tD1 = 0, sl = 0;
       if constexpr (NS == 2) {
-        mbar_wait(&acc_empty[rd.i], rd.ph);                          // the epilogue has read this D1 buffer
-        tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
-        rd.next();
+        if (!p.wide) {
+          mbar_wait(&acc_empty[rd.i], rd.ph);                        // the epilogue has read this D1 buffer
+          tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+          rd.next();
+        }
       } else {
         mbar_wait(&acc_empty[as], accph);
         tacc = tmem + as * acc_stride;
@@ -730,14 +840,19 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
             if (ks == 0) {
               sl = rs.i;
               mbar_wait(&slot_empty[sl], rs.ph);                      // the epilogue has drained this D0 slot
-              tD0 = tmem + sl * (uint32_t)NT;
+              tD0 = tmem + sl * (uint32_t)p.slot_cols;
               rs.next();
             }
             tc_fence_after();
             if (elect_one()) {
               const uint32_t acc0 = ks ? 1u : 0u, acc1 = first ? 0u : 1u;
-              if (ntap_b == 3) issue_band_f32<3, SPK>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
-              else issue_band_f32<1>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
+              if (p.wide) {
+                if (ntap_b == 3) issue_band_f32w<3, SPK>(a_base, a_plane, b_addr, tD0, (uint32_t)NT, idesc_w, idesc, acc0, b_rel, &a_empty[st]);
+                else issue_band_f32w<1>(a_base, a_plane, b_addr, tD0, (uint32_t)NT, idesc_w, idesc, acc0, b_rel, &a_empty[st]);
+              } else {
+                if (ntap_b == 3) issue_band_f32<3, SPK>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
+                else issue_band_f32<1>(a_base, a_plane, b_addr, b_plane, tD0, tD1, idesc, acc0, acc1, b_rel, &a_empty[st]);
+              }
             }
             __syncwarp();
             ks += SPK ? 6 : ntap_b * 4;
@@ -771,14 +886,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
         if (p.acc_stages == 2) { as ^= 1u; if (as == 0) accph ^= 1u; } else accph ^= 1u;
       }
     }
-  } else {
+  } else if (warp >= S_W_EPI) {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3, half = (warp - (S_TMA_WARPS + 1)) >> 2;
+    const int q = warp & 3, half = (warp - S_W_EPI) >> 2;
     if constexpr (NS == 2) {
+      reg_inc<208>();
       // fp32 mode: drain every finished band into registers, then D1, then math + stores (under the next tile's MMAs)
       const int steps = p.KC * nb;                              // issue_band calls per tile, ntap_b * 4 K steps each
       const int per = BAND_KSTEPS / (SPK ? 6 : ntap_b * 4);     // ... per D0 band: 1 (3x3), 3 (1x1) or 2 (super-pixel 3x3)
-      fp32_epilogue<S_EPI_NH, false>(p, tmem, total, (steps + per - 1) / per, q, half, lane, slot_full, slot_empty, acc_empty);
+      fp32_epilogue<S_EPI_NH, false>(p, tmem, total, (steps + per - 1) / per, q, half, lane, slot_full, slot_empty, acc_empty, epi_ss);
     } else {
       uint32_t as = 0, accph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -796,9 +912,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
       if (q == 0 && half == 0 && lane == 0) bulk_wait_all0();
     }
   }
+  else {
+    if constexpr (NS == 2) reg_dec<40>();             // idle warps of the MMA warpgroup
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == S_TMA_WARPS) tmem_dealloc_dyn(tmem, p.tmem_cols);
+  if (warp == S_W_MMA) tmem_dealloc_dyn(tmem, p.tmem_cols);
 }
 
 // =============================================================================== gather kernel
@@ -826,6 +945,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   uint64_t *slot_full = bars + 22, *slot_empty = bars + 28;              // fp32 mode: up to 6 D0 band slots (acc_empty = D1 buffers)
   unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 48);      // DCN sampling table (9*128*32 B)
+  float* epi_ss = reinterpret_cast<float*>(tab + (PROD == PROD_DCN ? 9 * TM * 32 : 0));     // fp32 epilogue: scale / shift staging
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -1125,6 +1245,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
    } else if (warp == W_MMA) {
     // ==================================================================== MMA issuer
     const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+    const uint32_t idesc_w = idesc_f16_f32(TM, 2 * NT);
     constexpr int R = AccR<NS>::value;
     constexpr int BAND_KB = BAND_KSTEPS / 4;                 // fp32 mode: K blocks per D0 band
     int s = 0;
@@ -1135,9 +1256,11 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       uint32_t tacc = 0, tD0 = 0, tD1 = 0, sl = 0;
       if constexpr (NS == 2) {
-        mbar_wait(&acc_empty[rd.i], rd.ph);
-        tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
-        rd.next();
+        if (!p.wide) {
+          mbar_wait(&acc_empty[rd.i], rd.ph);
+          tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+          rd.next();
+        }
       } else {
         mbar_wait(&acc_empty[as], accph);
         tacc = tmem + as * acc_stride;
@@ -1153,12 +1276,15 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
           if (kin == 0) {
             sl = rs.i;
             mbar_wait(&slot_empty[sl], rs.ph);
-            tD0 = tmem + sl * (uint32_t)NT;
+            tD0 = tmem + sl * (uint32_t)p.slot_cols;
             rs.next();
           }
           tc_fence_after();
           if (elect_one()) {
-            if (!(p.dbg & 16)) issue_kblock_f32(a0, a_plane, b0, b_plane, tD0, tD1, idesc, kin ? 1u : 0u, kb ? 1u : 0u);
+            if (!(p.dbg & 16)) {
+              if (p.wide) issue_kblock_f32w(a0, a_plane, b0, tD0, (uint32_t)NT, idesc_w, idesc, kin ? 1u : 0u);
+              else issue_kblock_f32(a0, a_plane, b0, b_plane, tD0, tD1, idesc, kin ? 1u : 0u, kb ? 1u : 0u);
+            }
             mma_commit(&empty[s]);
             if (kin + 1 == BAND_KB || kb == nkb - 1) mma_commit(&slot_full[sl]);
           }
@@ -1193,7 +1319,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
       else reg_inc<208>();
       constexpr int BAND_KB = BAND_KSTEPS / 4;
       fp32_epilogue<1, true, (WIDE || PROD != PROD_DCN) ? 8 : 4>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane,
-                                                                  slot_full, slot_empty, acc_empty);
+                                                                  slot_full, slot_empty, acc_empty, epi_ss);
     } else {
       uint32_t as = 0, accph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -1250,6 +1376,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
   uint64_t* xbar = bars + 21;
   uint64_t *slot_full = bars + 22, *slot_empty = bars + 28;
   unsigned char* tab = reinterpret_cast<unsigned char*>(bars + 48);      // sampling table (9*128*32 B)
+  float* epi_ss = reinterpret_cast<float*>(tab + 9 * TM * 32);           // fp32 epilogue: scale / shift staging
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -1452,7 +1579,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
     const int q = warp & 3;
     if constexpr (NS == 2) {
       constexpr int BAND_KB = BAND_KSTEPS / 4;
-      fp32_epilogue<1, true, WIDE ? 8 : 4>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane, slot_full, slot_empty, acc_empty);
+      fp32_epilogue<1, true, WIDE ? 8 : 4>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane, slot_full, slot_empty, acc_empty, epi_ss);
     } else {
       uint32_t as = 0, accph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -1490,6 +1617,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
     } else if (warp == 21) {
       // ==================================================================== MMA issuer
       const uint32_t idesc = NS == 2 ? idesc_f16_f32(TM, NT) : idesc_bf16_f32(TM, NT);
+      const uint32_t idesc_w = idesc_f16_f32(TM, 2 * NT);
       constexpr int BAND_KB = BAND_KSTEPS / 4;
       int s = 0;
       uint32_t ph = 0, as = 0, accph = 1;
@@ -1498,9 +1626,11 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         uint32_t tacc = 0, tD0 = 0, tD1 = 0, sl = 0;
         if constexpr (NS == 2) {
-          mbar_wait(&acc_empty[rd.i], rd.ph);
-          tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
-          rd.next();
+          if (!p.wide) {
+            mbar_wait(&acc_empty[rd.i], rd.ph);
+            tD1 = tmem + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
+            rd.next();
+          }
         } else {
           mbar_wait(&acc_empty[as], accph);
           tacc = tmem + as * (uint32_t)NT;
@@ -1513,12 +1643,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
             if (kin == 0) {
               sl = rs.i;
               mbar_wait(&slot_empty[sl], rs.ph);
-              tD0 = tmem + sl * (uint32_t)NT;
+              tD0 = tmem + sl * (uint32_t)p.slot_cols;
               rs.next();
             }
             tc_fence_after();
             if (elect_one()) {
-              issue_kblock_f32(a0, a_plane, b0, b_plane, tD0, tD1, idesc, kin ? 1u : 0u, kb ? 1u : 0u);
+              if (p.wide) issue_kblock_f32w(a0, a_plane, b0, tD0, (uint32_t)NT, idesc_w, idesc, kin ? 1u : 0u);
+              else issue_kblock_f32(a0, a_plane, b0, b_plane, tD0, tD1, idesc, kin ? 1u : 0u, kb ? 1u : 0u);
               mma_commit(&empty[s]);
               if (kin + 1 == BAND_KB || kb == nkb - 1) mma_commit(&slot_full[sl]);
             }
@@ -1596,10 +1727,23 @@ static void plan_acc(ConvP& p, int NS, bool short_k = false) {
     // fp32 mode (band-drain accumulation): D0 band slots + D1 buffers, NT <= 128 columns each.  The MMA warp can
     // run as many bands ahead of the epilogue warps as there are slots, which is what hides the previous tile's
     // scale / activation / store phase: as many as the 512 columns give (3 + 1 for 128-wide tiles, 6 + 2 below)
-    const int units = 512 / p.NT;
-    p.nd1 = units >= 8 ? 2 : 1;
-    p.nslots = units - p.nd1 > 6 ? 6 : units - p.nd1;
-    need = (p.nslots + p.nd1) * p.NT;
+    // Wide form (issue_kblock_f32w) for tiles of up to 64 columns: slots of [D0 | D1], no D1 buffers -- 4 slots at
+    // NT = 64, 6 below.  Measured (tools/wide_bench.py): 64 -> 64 3x3 163 -> 147 us, offset / mask convolutions (NT = 32)
+    // 79 -> 66 us; 128-wide tiles would be left with 2 slots and lose (141 -> 152 us, head 893 -> 965 us), so they keep
+    // the three-MMA form.  Debug flag 16384 disables the wide form, 32768 forces it for 128-wide tiles as well.
+    p.wide = !(p.dbg & 16384) && (p.NT <= 64 || (p.dbg & 32768));
+    if (p.wide) {
+      p.slot_cols = 2 * p.NT;
+      p.nd1 = 0;
+      p.nslots = 512 / p.slot_cols > 6 ? 6 : 512 / p.slot_cols;
+      need = p.nslots * p.slot_cols;
+    } else {
+      const int units = 512 / p.NT;
+      p.slot_cols = p.NT;
+      p.nd1 = units >= 8 ? 2 : 1;
+      p.nslots = units - p.nd1 > 6 ? 6 : units - p.nd1;
+      need = (p.nslots + p.nd1) * p.NT;
+    }
   }
   int c = 32;
   while (c < need) c <<= 1;
@@ -1619,7 +1763,7 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   p.b_resident = 0;
   if (p.n_tiles == 1 && p.nkb <= S_MAX_SB && p.nkb >= min_sb && !(p.dbg & 2048)) {
     const int stg = (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 16384 * NS : 0;
-    const int fx = 1024 + 1024 + stg;
+    const int fx = 1024 + 1024 + EPI_SS_BYTES + stg;
     if (2 * a_stage + p.nkb * b_stage + fx <= SMEM_LIMIT) {
       p.b_resident = 1;
       p.stg_bytes = stg;
@@ -1632,7 +1776,7 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   // (fp32 mode: measured no gain -- the hi/lo tile needs 32 KB that the weight ring uses better)
   for (int with_stg = p.b_resident ? -1 : (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 1 : 0; with_stg >= 0; --with_stg) {
     p.stg_bytes = with_stg ? 16384 * NS : 0;
-    fixed = 1024 + 1024 + p.stg_bytes;
+    fixed = 1024 + 1024 + EPI_SS_BYTES + p.stg_bytes;
     SB = 4; SA = 3;
     while (SB > min_sb && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SB;
     while (SA > 1 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SA;
@@ -1665,7 +1809,7 @@ template <int PROD, int NS>
 static int launch_gather(ConvP& p, cudaStream_t st) {
   const int a_bytes = TM * 128 * NS, b_bytes = p.NT * 128 * NS;
   p.stg_bytes = NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8) ? 16384 * NS : 0;
-  const int fixed = 1024 + 512 + p.stg_bytes + (PROD == PROD_DCN ? 9 * TM * 32 : 0);
+  const int fixed = 1024 + 512 + EPI_SS_BYTES + p.stg_bytes + (PROD == PROD_DCN ? 9 * TM * 32 : 0);
   // weights resident in shared memory when one CTA sees a single N tile and they leave room for
   // >= 2 A stages: no per-K-block weight copy (a single thread's bulk copies serialise, ~530 clk each)
   p.b_resident = p.n_tiles == 1 && fixed + p.nkb * b_bytes + 2 * a_bytes <= SMEM_LIMIT;
@@ -1700,7 +1844,7 @@ template <int NS>
 static int try_launch_dcn_tile(ConvP& p, cudaStream_t st) {
   if ((p.dbg & 32) || p.Ho % 8 || p.Wo % 16 || p.n_tiles != 1) return -1;
   const int a_bytes = TM * 128 * NS, b_bytes = p.NT * 128 * NS;
-  const int fixed = 1024 + 512 + 9 * TM * 32;
+  const int fixed = 1024 + 512 + EPI_SS_BYTES + 9 * TM * 32;
   for (int SA = NS == 2 ? 2 : 3; SA >= 2; --SA) {
     for (int h = 3; h >= 2; --h) {
       const int LH = 8 + 2 * h, LW = 16 + 2 * h;

@@ -14,7 +14,7 @@ def bench(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 cfgs = [(64, 64, 64, 96, 3), (64, 128, 128, 48, 3), (64, 256, 256, 24, 3), (32, 64, 768, 96, 3), (64, 128, 64, 96, 1)]
 ns_list = [int(a) for a in sys.argv[1:]] or [2, 1]
-NTF = int(os.environ.get("NT64", "0")) * 64
+NTF = int(os.environ.get("NT64", "0")) * 64 | int(os.environ.get("DBG", "0"))
 for ns in ns_list:
     for B, Ci, Co, H, k in cfgs:
         _lib.load().sgta_debug_flags(NTF)

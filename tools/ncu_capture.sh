@@ -8,7 +8,7 @@
 tag=$1; rx=$2; n=$3; top=${4:-4}; shift 4
 rep=/tmp/$tag
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$rx" -c "$n" \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$rx" --launch-skip "${SKIP:-0}" -c "$n" \
     -f -o $rep python bench.py --profile-pass --no-cpu-baseline "$@" > gpurun_out/${tag}_ncu.log 2>&1
 ncu -i $rep.ncu-rep --page raw --csv > gpurun_out/${tag}_raw.csv 2>/dev/null
 python - "$tag" "$top" <<'EOF' > /tmp/${tag}_top.txt
