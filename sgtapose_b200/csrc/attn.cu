@@ -56,6 +56,8 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
   float* Vs = att_smem + (size_t)nk * S;
   const int h = blockIdx.y, b = blockIdx.z;
   const int HD = heads * D;
+  pdl_trigger();
+  pdl_wait();
   stage_kv<D>(Ks, Vs, k + (long long)b * nk * HD, v + (long long)b * nk * HD, nk, HD, h);
   __syncthreads();
 
@@ -153,6 +155,7 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
   const int nvec = nk * V4;
   const int grp = warp % WG, ks = warp / WG;
 
+  pdl_trigger();
   if (pos) {
     for (int r = warp; r < ATT_ROWS; r += ATB_WARPS) {
       const int i = row0 + r;
@@ -161,6 +164,7 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
       for (int j = lane; j < nk; j += 32) Ps[r * nk_pad + j] = __ldg(prow + j) * LOG2E;
     }
   }
+  pdl_wait();                                   // pos_embed is a parameter; q / k / v come from the preceding kernels
   float4 kreg[PF], vreg[PF], qreg = make_float4(0.f, 0.f, 0.f, 0.f);
   auto prefetch = [&](int b) {
     const float* kb = k + (long long)b * nk * HD + h * D;
@@ -319,11 +323,13 @@ attn_fwd_rows_kernel(const float* __restrict__ q, const float* __restrict__ k, c
   const int b_begin = blockIdx.z * b_per_cta, b_end = min(B, b_begin + b_per_cta);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  pdl_trigger();
   for (int r = warp; r < ATT_ROWS; r += ATB_WARPS) {
     const int i = min(row0 + r, nq - 1);
     const float* prow = pos ? pos + ((long long)h * nq + i) * nk : nullptr;
     for (int j = lane; j < nk; j += 32) Ps[r * nk_pad + j] = prow ? __ldg(prow + j) * LOG2E : 0.f;
   }
+  pdl_wait();                                   // pos_embed is a parameter; q / k / v come from the preceding kernels
   float4 kreg[PF], vreg[PF], qreg = make_float4(0.f, 0.f, 0.f, 0.f);
   auto prefetch = [&](int b) {
     const long long kv0 = KVHM ? ((long long)b * heads + h) * nk * D : (long long)b * nk * HD + h * D;
@@ -550,8 +556,8 @@ static int launch_fwd(const float* q, const float* k, const float* v, const floa
         zc = cdiv(B, bpc);
         auto kern = kvhm ? attn_fwd_rows_kernel<D, true> : attn_fwd_rows_kernel<D, false>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
-        kern<<<dim3(cdiv(nq, ATT_ROWS), heads, zc), ATB_THREADS, smem_r, st>>>(q, k, v, pos, out, B, heads, nq, nk, nk_pad,
-                                                                             bpc, inv_scale);
+        launch_k(kern, dim3(cdiv(nq, ATT_ROWS), heads, zc), ATB_THREADS, smem_r, st, q, k, v, pos, out, B, heads, nq, nk, nk_pad,
+                 bpc, inv_scale);
         return check_launch("attn_fwd_rows_kernel");
       }
     }
@@ -562,8 +568,8 @@ static int launch_fwd(const float* q, const float* k, const float* v, const floa
     zchunks = cdiv(B, b_per_cta);
     cudaFuncSetAttribute(attn_fwd_batched_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
     dim3 grid(cdiv(nq, ATT_ROWS), heads, zchunks);
-    attn_fwd_batched_kernel<D><<<grid, ATB_THREADS, smem_b, st>>>(q, k, v, pos, out, B, heads, nq, nk, nk_pad,
-                                                                b_per_cta, inv_scale);
+    launch_k(attn_fwd_batched_kernel<D>, grid, ATB_THREADS, smem_b, st, q, k, v, pos, out, B, heads, nq, nk, nk_pad,
+             b_per_cta, inv_scale);
     return check_launch("attn_fwd_batched_kernel");
   }
   size_t smem = sizeof(float) * 2 * (size_t)nk * KPad<D>::stride;
@@ -571,7 +577,7 @@ static int launch_fwd(const float* q, const float* k, const float* v, const floa
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(cdiv(nq, ATT_ROWS), heads, B);
-  attn_fwd_kernel<D><<<grid, ATT_WARPS * 32, smem, st>>>(q, k, v, pos, out, heads, nq, nk, inv_scale);
+  launch_k(attn_fwd_kernel<D>, grid, ATT_WARPS * 32, smem, st, q, k, v, pos, out, heads, nq, nk, inv_scale);
   return check_launch("attn_fwd_kernel");
 }
 

@@ -12,6 +12,7 @@ namespace sgta {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
+int debug_flags();                        // current sgta_debug_flags value (kernel experiments)
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -45,5 +46,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (EXPERIMENT, off by default: debug flag 131072 turns it on).  Every kernel of the
+// inference step starts with pdl_trigger() (its dependents may be scheduled as soon as all of its own CTAs are running)
+// and, BEFORE its first access to anything a predecessor writes or reads, pdl_wait() (returns when the preceding grid
+// has completed and flushed); launch_k then adds the programmatic-stream-serialization attribute, so the next kernel's
+// CTAs take the SMs the current one frees, set up barriers / TMEM / constant staging and sit in pdl_wait() (programmatic
+// edges inside the CUDA graph).  Measured on B200 over the whole step (158 launches, same box, alternating runs):
+// 14.39 ms with the attribute vs 13.97 ms without -- 2.7 us per kernel boundary SLOWER, all 150 GPU tests green either
+// way.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at = {};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = (debug_flags() & 131072) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace sgta

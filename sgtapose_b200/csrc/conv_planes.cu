@@ -46,7 +46,9 @@ template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("se
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 constexpr int S_TMA_WARPS = 4;                           // bulk copies issued by ONE warp serialise (~530 clk
                                                          // each, tests/cuda/tma_bw_probe.cu): spread them over 4
-constexpr int S_EPI_NH = 2;                              // epilogue warps per TMEM lane quadrant (each takes half the columns)
+// epilogue warps per TMEM lane quadrant (each takes half the columns).  Measured with 4 (16 epilogue warps of 96
+// registers): 1x1 128 -> 64 97 -> 82 us, but 128 -> 128 3x3 131 -> 143 us and the head conv 708 -> 817 us: stays 2.
+constexpr int S_EPI_NH = 2;
 // warps: [4 TMA | MMA issuer, 3 idle | 4 * S_EPI_NH epilogue] -- whole warpgroups, so fp32 mode can hand the registers
 // of the first two groups to the epilogue warps (setmaxnreg): at 128 registers the band-drain epilogue spilled
 constexpr int S_W_MMA = S_TMA_WARPS, S_W_EPI = 8;
@@ -101,6 +103,7 @@ __device__ __forceinline__ int tile_row_m(const ConvP& p, int t, int row) {
 }
 
 static int g_dbg = 0;
+int debug_flags() { return g_dbg; }
 
 // m -> (px, py, b) of the zero-bordered output frame, without integer division
 __device__ __forceinline__ void decode_row(const ConvP& p, int m, int& px, int& py, int& b) {
@@ -414,28 +417,37 @@ __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int 
 #pragma unroll
       for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
     }
+    if (!e.staged) {       // 16 channels = one aligned 32-byte sector per plane in every layout: STG.256
+      if (p.epi == SGTA_EPI_PL) pl_store16<NS>(p.y, n >> 6, e.m, (n & 63) >> 3, o);
+      else if (p.epi == SGTA_EPI_SC) sc_store16<NS>(p.y, e.m, n, o);
+      else sc_store16<NS>(p.y, sp2sc_row(p, e, n >> 4), 0, o);
+      return;
+    }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2; ++h) {          // staged: the tile's shared-memory image, bulk-stored by the caller
       float f[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = o[8 * h + j];
       const int ch = n + 8 * h;
-      if (e.staged) {
-        uint4 e0, e1;
-        encode8<NS>(f, e0, e1);
-        if (!e.valid) { e0 = make_uint4(0, 0, 0, 0); e1 = e0; }
-        const uint32_t a = e.srow + ((((uint32_t)(ch & 63) >> 3) ^ e.sxor) << 4);
-        sts128(a, e0);
-        if (NS == 2) sts128(a + 16384u, e1);
-      } else if (p.epi == SGTA_EPI_PL) pl_store8<NS>(p.y, ch >> 6, e.m, (ch & 63) >> 3, f);
-      else if (p.epi == SGTA_EPI_SC) sc_store8<NS>(p.y, e.m, ch, f);
-      else sc_store8<NS>(p.y, sp2sc_row(p, e, ch >> 4), ch & 15, f);
+      uint4 e0, e1;
+      encode8<NS>(f, e0, e1);
+      if (!e.valid) { e0 = make_uint4(0, 0, 0, 0); e1 = e0; }
+      const uint32_t a = e.srow + ((((uint32_t)(ch & 63) >> 3) ^ e.sxor) << 4);
+      sts128(a, e0);
+      if (NS == 2) sts128(a + 16384u, e1);
     }
   } else if (p.epi == SGTA_EPI_F32ROWS) {
     if (!e.inP) return;
-    float4* dst = reinterpret_cast<float4*>(p.yf + (size_t)e.m * p.ldyf + n);
+    float* dst = p.yf + (size_t)e.m * p.ldyf + n;
+    if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      for (int j = 0; j < 2; ++j)
+        stg256(dst + 8 * j, make_uint4(__float_as_uint(o[8 * j]), __float_as_uint(o[8 * j + 1]), __float_as_uint(o[8 * j + 2]), __float_as_uint(o[8 * j + 3])),
+               make_uint4(__float_as_uint(o[8 * j + 4]), __float_as_uint(o[8 * j + 5]), __float_as_uint(o[8 * j + 6]), __float_as_uint(o[8 * j + 7])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
   } else {   // SGTA_EPI_NCHW: fp32 [B, n_valid, Ho, Wo]
     if (!e.valid) return;
     const size_t hw = (size_t)p.Ho * p.Wo;
@@ -504,10 +516,11 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
     }
     const uint32_t ss = smem_u32(epi_ss) + ss_buf * 1024u;
     float acc[NG][16];
+    float acc1[NG <= 2 ? NG : 1][16];                 // wide form, NG <= 2: the D1 halves of the band slots
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[g][j] = 0.f;
+      for (int j = 0; j < 16; ++j) { acc[g][j] = 0.f; if (NG <= 2) acc1[NG <= 2 ? g : 0][j] = 0.f; }
     for (int bnd = 0; bnd < nbands; ++bnd) {
       if (BACKOFF) mbar_wait_backoff(&slot_full[rs.i], rs.ph);
       else mbar_wait(&slot_full[rs.i], rs.ph);
@@ -518,7 +531,14 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
             if ((g0 + g) * 16 < NT) {
-              if constexpr (NG <= 4) {
+              if constexpr (NG <= 2) {                     // D1 summed on its own, scaled in once per tile
+                uint32_t d[16], e1[16];
+                tmem_ld16(ts + (uint32_t)((g0 + g) * 16), d);
+                tmem_ld16(ts + (uint32_t)(NT + (g0 + g) * 16), e1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { acc[g][j] += __uint_as_float(d[j]); acc1[g][j] += __uint_as_float(e1[j]); }
+              } else if constexpr (NG <= 4) {
                 uint32_t d[16], e1[16];
                 tmem_ld16(ts + (uint32_t)((g0 + g) * 16), d);
                 tmem_ld16(ts + (uint32_t)(NT + (g0 + g) * 16), e1);
@@ -556,7 +576,14 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
       if (lane == 0) mbar_arrive(&slot_empty[rs.i]);
       rs.next();
     }
-    if (!wide) {
+    if (wide) {
+      if constexpr (NG <= 2) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[g][j] = fmaf(acc1[g][j], LO_INV, acc[g][j]);
+      }
+    } else {
       if (!(p.dbg & 4)) {
         const uint32_t td = lane_base + (uint32_t)(p.nslots + (int)rd.i) * (uint32_t)NT;
 #pragma unroll
@@ -587,13 +614,11 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
           if (j * 32 < NT) {
             float lo8[8], hi8[8];
             stem_pixel(p, acc[NG >= 2 ? 2 * j : 0], acc[NG >= 2 ? 2 * j + 1 : 0], lo8, hi8);
-            if (p.epi == SGTA_EPI_STEM) {
-              sc_store8<2>(p.y, e.m, 0, lo8);
-              sc_store8<2>(p.y, e.m, 8, hi8);
-            } else {
-              pl_store8<2>(p.y, 0, e.m, 2 * j, lo8);
-              pl_store8<2>(p.y, 0, e.m, 2 * j + 1, hi8);
-            }
+            float o16[16];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { o16[c] = lo8[c]; o16[8 + c] = hi8[c]; }
+            if (p.epi == SGTA_EPI_STEM) sc_store16<2>(p.y, e.m, 0, o16);
+            else pl_store16<2>(p.y, 0, e.m, 2 * j, o16);
           }
         }
       }
@@ -724,6 +749,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   float* epi_ss = reinterpret_cast<float*>(bars + 128);         // scale / shift staging of the fp32 epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&a_full[s], NS); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < S_MAX_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -735,6 +761,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                          // barriers / TMEM are set up: now the inputs must be complete
   const uint32_t tmem = *tmem_slot;
   const uint32_t acc_stride = (uint32_t)((p.acc_r + NS - 1) * NT);
   const int total = p.m_tiles * p.n_tiles;
@@ -948,6 +975,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
   float* epi_ss = reinterpret_cast<float*>(tab + (PROD == PROD_DCN ? 9 * TM * 32 : 0));     // fp32 epilogue: scale / shift staging
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&full[s], G_PROD_WARPS + (p.b_resident ? 0 : 1)); mbar_init(&empty[s], 1); }
     mbar_init(b_ready, 1);
@@ -959,6 +987,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_slot;
   const uint32_t acc_stride = (uint32_t)((p.acc_r + NS - 1) * NT);
   const int total = p.m_tiles * p.n_tiles;
@@ -1379,6 +1408,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
   float* epi_ss = reinterpret_cast<float*>(tab + 9 * TM * 32);           // fp32 epilogue: scale / shift staging
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&full[s], D_PROD_WARPS + 1); mbar_init(&empty[s], 1); }
     mbar_init(xbar, D_PROD_WARPS);
@@ -1390,6 +1420,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_slot;
   const int total = p.tiles_x * p.tiles_y * p.x.B;             // n_tiles == 1
   const int nkb = p.nkb;
@@ -1727,10 +1758,11 @@ static void plan_acc(ConvP& p, int NS, bool short_k = false) {
     // fp32 mode (band-drain accumulation): D0 band slots + D1 buffers, NT <= 128 columns each.  The MMA warp can
     // run as many bands ahead of the epilogue warps as there are slots, which is what hides the previous tile's
     // scale / activation / store phase: as many as the 512 columns give (3 + 1 for 128-wide tiles, 6 + 2 below)
-    // Wide form (issue_kblock_f32w) for tiles of up to 64 columns: slots of [D0 | D1], no D1 buffers -- 4 slots at
-    // NT = 64, 6 below.  Measured (tools/wide_bench.py): 64 -> 64 3x3 163 -> 147 us, offset / mask convolutions (NT = 32)
-    // 79 -> 66 us; 128-wide tiles would be left with 2 slots and lose (141 -> 152 us, head 893 -> 965 us), so they keep
-    // the three-MMA form.  Debug flag 16384 disables the wide form, 32768 forces it for 128-wide tiles as well.
+    // Wide form (issue_kblock_f32w): slots of [D0 | D1], no D1 buffers -- 4 slots at NT = 64, 6 below, 2 at 128.
+    // Measured (tools/wide_bench.py): 64 -> 64 3x3 163 -> 147 us, offset / mask convolutions (NT = 32) 79 -> 66 us;
+    // 128-wide tiles are left with 2 slots: 1-2 % faster on long K (128 -> 128 3x3 130.7 -> 129.0 us), slower on the
+    // K = 576 head convolution (710 -> 730 us), and their D1 would be rounded into the sum once per band instead of
+    // once per tile -- they keep the three-MMA form.  Debug flag 16384 disables the wide form, 32768 forces it everywhere.
     p.wide = !(p.dbg & 16384) && (p.NT <= 64 || (p.dbg & 32768));
     if (p.wide) {
       p.slot_cols = 2 * p.NT;
@@ -1797,10 +1829,10 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   const int grid = total < sms ? total : sms;
   if (p.spk) {
     cudaFuncSetAttribute(conv_shift_kernel<NS, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_shift_kernel<NS, 1, 1><<<grid, S_THREADS, smem, st>>>(p);
+    launch_k(conv_shift_kernel<NS, 1, 1>, grid, S_THREADS, smem, st, p);
   } else {
     cudaFuncSetAttribute(conv_shift_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_shift_kernel<NS, 1><<<grid, S_THREADS, smem, st>>>(p);
+    launch_k(conv_shift_kernel<NS, 1>, grid, S_THREADS, smem, st, p);
   }
   return check_launch("conv_shift_kernel");
 }
@@ -1831,10 +1863,10 @@ static int launch_gather(ConvP& p, cudaStream_t st) {
   if (NS == 2 && PROD == PROD_DCN && p.NT > 64) {
     constexpr int W = (NS == 2 && PROD == PROD_DCN) ? 1 : 0;     // (only this combination instantiates the WIDE variant)
     cudaFuncSetAttribute(conv_gather_kernel<PROD, NS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_gather_kernel<PROD, NS, W><<<grid, GThreads<PROD>::value, smem, st>>>(p);
+    launch_k(conv_gather_kernel<PROD, NS, W>, grid, GThreads<PROD>::value, smem, st, p);
   } else {
     cudaFuncSetAttribute(conv_gather_kernel<PROD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_gather_kernel<PROD, NS><<<grid, GThreads<PROD>::value, smem, st>>>(p);
+    launch_k(conv_gather_kernel<PROD, NS>, grid, GThreads<PROD>::value, smem, st, p);
   }
   return check_launch("conv_gather_kernel");
 }
@@ -1859,10 +1891,10 @@ static int try_launch_dcn_tile(ConvP& p, cudaStream_t st) {
       const int grid = total < sms ? total : sms;
       if (NS == 2 && p.NT > 64) {
         cudaFuncSetAttribute(dcn_tile_kernel<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        dcn_tile_kernel<NS, 1><<<grid, D_THREADS, smem, st>>>(p);
+        launch_k(dcn_tile_kernel<NS, 1>, grid, D_THREADS, smem, st, p);
       } else {
         cudaFuncSetAttribute(dcn_tile_kernel<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        dcn_tile_kernel<NS, 0><<<grid, D_THREADS, smem, st>>>(p);
+        launch_k(dcn_tile_kernel<NS, 0>, grid, D_THREADS, smem, st, p);
       }
       return check_launch("dcn_tile_kernel");
     }
@@ -1945,7 +1977,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
   p.dbg = g_dbg;
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
-  p.act = act; p.stride = stride; p.sx = stride; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
+  p.act = act; p.stride = stride; p.sx = stride; p.NT = NT; p.n_tiles = Cout / NT;
   const int pad = ksize / 2;
   const int Ho = (x->H + 2 * pad - ksize) / stride + 1, Wo = (x->W + 2 * pad - ksize) / stride + 1;
   SGTA_REQUIRE(Ho > 0 && Wo > 0, "sgta_planes_conv: empty output");
@@ -1972,7 +2004,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
       // EPI_SP2SC = level0 over super-pixels: the weights come from planes.superpixel_weight (gin = gout = 4, 16
       // channels), whose neighbour taps are zero outside one pixel -- those K steps are not issued
       p.spk = epi == SGTA_EPI_SP2SC && ksize == 3 && Cin == 64 && !(p.dbg & 512);
-      if (NS == 2 && NT == 128 && p.nkb <= 9) plan_acc(p, NS, true);
+      plan_acc(p, NS);
       const int Wp = x->W + 2;
       SGTA_REQUIRE(x->guard >= Wp + 1 + 8 && x->rows >= (int64_t)x->guard + (int64_t)p.m_tiles * TM + Wp + 16 + 8,
                    "sgta_planes_conv: input guard rows too small for the halo");
@@ -1980,6 +2012,7 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
     }
     SGTA_REQUIRE(ksize == 3, "sgta_planes_conv: PL strided kernels are 3x3");
     p.taps = 9; p.nkb = 9 * p.KC;
+    plan_acc(p, NS);
     return NS == 2 ? launch_gather<PROD_STRIDE, 2>(p, st) : launch_gather<PROD_STRIDE, 1>(p, st);
   }
   // SC input: K blocks described by the caller through sgta_planes_conv_sc
@@ -2002,7 +2035,7 @@ extern "C" int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, cons
   p.x = make_view(x);
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
   SGTA_REQUIRE(stride >= 1 && stride_x >= 1, "sgta_planes_conv_sc: strides must be positive");
-  p.act = act; p.stride = stride; p.sx = stride_x; p.NT = NT; p.n_tiles = Cout / NT; plan_acc(p, NS);
+  p.act = act; p.stride = stride; p.sx = stride_x; p.NT = NT; p.n_tiles = Cout / NT; p.nkb = nkb; plan_acc(p, NS);
   const long long P = (long long)x->B * (Ho + 2) * (Wo + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv_sc: too many pixels");
   p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.m_tiles = cdiv(P, TM);
@@ -2030,6 +2063,7 @@ extern "C" int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, co
   p.om = (const float*)offset_mask;
   p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
   p.act = relu ? SGTA_ACT_RELU : SGTA_ACT_NONE; p.stride = 1; p.NT = NT; p.n_tiles = Cout / NT;
+  p.KC = Cin / 64; p.nkb = 9 * p.KC;
   plan_acc(p, NS);
   const long long P = (long long)x->B * (x->H + 2) * (x->W + 2);
   SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_dcn: too many pixels");

@@ -409,10 +409,12 @@ decode_peaks_f32_kernel(const float* __restrict__ hm, const float* __restrict__ 
   float* bufA = reinterpret_cast<float*>(dsm);
   float* bufB = bufA + plane_floats;
   Cand* cands = reinterpret_cast<Cand*>(bufB);          // aliases bufB (dead once the scans are done)
+  pdl_trigger();
   if (tid == 0) {
     s_count = 0; s_nund = 0; s_nacc = 0; s_min_ok = 1; s_nhot = 0; s_finite = 1;
     s_box[0] = h; s_box[1] = -1; s_box[2] = w; s_box[3] = -1;
   }
+  pdl_wait();
   __syncthreads();
 
   // phase 0
@@ -982,9 +984,9 @@ extern "C" int sgta_decode_peaks(const void* hm, const void* reg, const void* tr
     auto kern = packed ? decode_peaks_f32_kernel<true> : decode_peaks_f32_kernel<false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<B * C, 256, smem, (cudaStream_t)stream>>>(
-        (const float*)hm, (const float*)reg, (const float*)tracking, (float*)scores, (long long*)inds,
-        (long long*)xs, (long long*)ys, (float*)cts_wreg, (float*)trk, gw, gf, C, h, w, (int)plane);
+    launch_k(kern, B * C, 256, smem, (cudaStream_t)stream,
+             (const float*)hm, (const float*)reg, (const float*)tracking, (float*)scores, (long long*)inds,
+             (long long*)xs, (long long*)ys, (float*)cts_wreg, (float*)trk, gw, gf, C, h, w, (int)plane);
     return check_launch("decode_peaks_f32_kernel");
   }
   return launch_peaks_f64(hm, reg, tracking, scores, inds, xs, ys, cts_wreg, trk, gw, B, C, h, w,

@@ -124,6 +124,29 @@ __device__ __forceinline__ void pl_store8(const View& v, int chunk, long long p,
   *reinterpret_cast<uint4*>(v.base + pl_offset(v, 0, chunk, p, c8)) = a;
   if (NS == 2) *reinterpret_cast<uint4*>(v.base + pl_offset(v, 1, chunk, p, c8)) = b;
 }
+// 32-byte store (STG.256, sm_100): lo = the 16 bytes at the lower address
+__device__ __forceinline__ void stg256(void* ptr, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+// 16 consecutive channels (groups c8, c8 + 1, c8 even) of a PL view: the swizzle XORs the group index with the row's low
+// bits, so the pair stays inside one aligned 32-byte sector (swapped when the row is odd) -- one STG.256 per plane
+// instead of two STG.128: half the store instructions and half the L1 wavefronts of the epilogues
+template <int NS>
+__device__ __forceinline__ void pl_store16(const View& v, int chunk, long long p, int c8, const float (&f)[16]) {
+  float f0[8], f1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { f0[j] = f[j]; f1[j] = f[8 + j]; }
+  uint4 a0, b0, a1, b1;
+  encode8<NS>(f0, a0, b0);
+  encode8<NS>(f1, a1, b1);
+  const long long r = v.guard + p;
+  const bool odd = r & 1;
+  unsigned char* dst = v.base + ((((size_t)v.chunk0 + chunk) * v.rows + r) << 7) + (size_t)((((c8 ^ (int)(r & 7)) & 6)) << 4);
+  stg256(dst, odd ? a1 : a0, odd ? a0 : a1);
+  if (NS == 2) stg256(dst + (((size_t)v.nchunks * v.rows) << 7), odd ? b1 : b0, odd ? b0 : b1);
+}
 template <int NS>
 __device__ __forceinline__ void sc_load8(const View& v, long long p, int c, float (&f)[8]) {
   uint4 a = __ldg(reinterpret_cast<const uint4*>(v.base + sc_offset(v, 0, p, c)));
@@ -137,6 +160,19 @@ __device__ __forceinline__ void sc_store8(const View& v, long long p, int c, con
   encode8<NS>(f, a, b);
   *reinterpret_cast<uint4*>(v.base + sc_offset(v, 0, p, c)) = a;
   if (NS == 2) *reinterpret_cast<uint4*>(v.base + sc_offset(v, 1, p, c)) = b;
+}
+
+// 16 consecutive channels of an SC view (c % 16 == 0: 32-byte aligned in every SC layout used, C in {16, 32})
+template <int NS>
+__device__ __forceinline__ void sc_store16(const View& v, long long p, int c, const float (&f)[16]) {
+  float f0[8], f1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { f0[j] = f[j]; f1[j] = f[8 + j]; }
+  uint4 a0, b0, a1, b1;
+  encode8<NS>(f0, a0, b0);
+  encode8<NS>(f1, a1, b1);
+  stg256(v.base + sc_offset(v, 0, p, c), a0, a1);
+  if (NS == 2) stg256(v.base + sc_offset(v, 1, p, c), b0, b1);
 }
 
 }  // namespace sgta

@@ -57,6 +57,8 @@ __global__ void pl_to_nchw_kernel(View x, float* __restrict__ dst, int C, int c_
 template <int NS>
 __global__ void pl_pack_stem_kernel(const float* __restrict__ img, const float* __restrict__ hm, View y, int b_off,
                                  int B, int border, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int HW = y.H * y.W;
@@ -79,6 +81,8 @@ __global__ void pl_pack_stem_kernel(const float* __restrict__ img, const float* 
 // ---- 2x2 / stride-2 max-pool ------------------------------------------------------------------
 template <int NS>
 __global__ void pl_maxpool2_kernel(View x, View y, int C, int xc_off, int yc_off, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int G = C / 8;
@@ -109,11 +113,13 @@ template <int NS>
 __global__ void __launch_bounds__(256)
 pl_upsample_add_kernel(View x, const float* __restrict__ w, View skip, int has_skip, View y, int C, int f) {
   extern __shared__ __align__(16) float ups_w[];
+  pdl_trigger();
   const int k = 2 * f, pad = f / 2, kk = k * k;
   for (int i = threadIdx.x; i < kk * C; i += 256) {
     const int c = i % C, t = i / C;
     ups_w[i] = __ldg(w + (long long)c * kk + t);
   }
+  pdl_wait();
   __syncthreads();
   const int G = C >> 3;
   const int b = blockIdx.z, oy0 = blockIdx.y * UPS_ROWS;
@@ -151,6 +157,70 @@ pl_upsample_add_kernel(View x, const float* __restrict__ w, View skip, int has_s
   }
 }
 
+// f = 2 (seven of the eight up-samplers of the network: dla.py:561-577 with f = 2): the output block
+// {2i-1, 2i} x {2j-1, 2j} reads the same four input pixels (i-1..i, j-1..j), so one thread loads them once (the zero
+// border of the frame stands in for the out-of-range ones) and produces the four outputs -- a quarter of the input
+// loads and of the address arithmetic of the general kernel.  Measured: 0.530 -> 0.519 ms over the 8 launches of a
+// step only -- the kernel is bound by memory latency (ncu: DRAM 32 %, L1 42 %, issue 55 %), not by instructions.
+// Same tap order per output as the general kernel: skip, then (i, j), (i, j-1), (i-1, j), (i-1, j-1).
+constexpr int UP2_ROWS = 4;            // input rows per CTA
+template <int NS>
+__global__ void __launch_bounds__(256)
+pl_upsample2_add_kernel(View x, const float* __restrict__ w, View skip, int has_skip, View y, int C) {
+  extern __shared__ __align__(16) float ups_w[];
+  pdl_trigger();
+  for (int i = threadIdx.x; i < 16 * C; i += 256) {
+    const int c = i % C, t = i / C;
+    ups_w[i] = __ldg(w + (long long)c * 16 + t);
+  }
+  pdl_wait();
+  __syncthreads();
+  const int G = C >> 3;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= (x.W + 1) * G) return;
+  const int j = t / G, g = t - j * G;
+  const int b = blockIdx.z;
+  const int i1 = min((int)(blockIdx.y + 1) * UP2_ROWS, x.H + 1);
+  for (int i = blockIdx.y * UP2_ROWS; i < i1; ++i) {
+    float v[2][2][8];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) load8<NS>(x, frame_row(x, b, i - 1 + dy, j - 1 + dx), g * 8, v[dy][dx]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int oy = 2 * i - 1 + a;
+      if (oy < 0 || oy >= y.H) continue;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int ox = 2 * j - 1 + bb;
+        if (ox < 0 || ox >= y.W) continue;
+        float acc[8];
+        const long long po = frame_row(y, b, oy, ox);
+        if (has_skip) load8<NS>(skip, po, g * 8, acc);
+        else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        }
+#pragma unroll
+        for (int dy = 1; dy >= 0; --dy)
+#pragma unroll
+          for (int dx = 1; dx >= 0; --dx) {
+            const int ky = a + 2 * (1 - dy), kx = bb + 2 * (1 - dx);
+            const float4* wt = reinterpret_cast<const float4*>(ups_w + (ky * 4 + kx) * C + g * 8);
+            const float4 w0 = wt[0], w1 = wt[1];
+            const float (&u)[8] = v[dy][dx];
+            acc[0] = fmaf(u[0], w0.x, acc[0]); acc[1] = fmaf(u[1], w0.y, acc[1]);
+            acc[2] = fmaf(u[2], w0.z, acc[2]); acc[3] = fmaf(u[3], w0.w, acc[3]);
+            acc[4] = fmaf(u[4], w1.x, acc[4]); acc[5] = fmaf(u[5], w1.y, acc[5]);
+            acc[6] = fmaf(u[6], w1.z, acc[6]); acc[7] = fmaf(u[7], w1.w, acc[7]);
+          }
+        store8<NS>(y, po, g * 8, acc);
+      }
+    }
+  }
+}
+
 // ---- super-pixel views ----------------------------------------------------------
 // A [rows][16 ch] SC map read as [rows / 4][4 px x 16 ch]: one 128-byte PL row per SUPER-PIXEL (channel index
 // j*16 + c for pixel j of the group), frame (H+2) x (W/4+2) with the usual one-(super-)pixel zero border, so
@@ -182,6 +252,8 @@ __global__ void pl_sc16_super4_kernel(View sc, View sp, int to_super, long long 
 template <int NS>
 __global__ void pl_gather_tokens_kernel(View x, int b_off, const long long* __restrict__ ids, float* __restrict__ rows,
                                      int C, int n, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int G = C / 8;
@@ -202,6 +274,8 @@ template <int NS>
 __global__ void __launch_bounds__(256)
 pl_scatter_tokens_kernel(View x, int b_off, const long long* __restrict__ ids, const float* __restrict__ rows, int C, int n) {
   extern __shared__ int s_ids[];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   for (int t = threadIdx.x; t < n; t += blockDim.x) s_ids[t] = (int)ids[(long long)b * n + t];
   __syncthreads();
@@ -266,8 +340,8 @@ extern "C" int sgta_planes_pack_stem(const void* img_f32, const void* hm_f32, co
                b_off >= 0 && B > 0 && b_off + B <= y->B, "sgta_planes_pack_stem: bad arguments");
   const long long total = (long long)B * y->H * y->W;
   View v = make_view(y);
-  NS_DISPATCH(y->nplanes, (pl_pack_stem_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                              (const float*)img_f32, (const float*)hm_f32, v, b_off, B, y->border, total)));
+  NS_DISPATCH(y->nplanes, launch_k(pl_pack_stem_kernel<NS>, cdiv(total, 256), 256, 0, (cudaStream_t)stream,
+                                   (const float*)img_f32, (const float*)hm_f32, v, b_off, B, y->border, total));
   return check_launch("pl_pack_stem_kernel");
 }
 
@@ -277,7 +351,7 @@ extern "C" int sgta_planes_maxpool2(const sgta_planes* x, int xc_off, const sgta
                "sgta_planes_maxpool2: bad arguments");
   const long long total = (long long)y->B * y->H * y->W * (C / 8);
   View vx = make_view(x), vy = make_view(y);
-  NS_DISPATCH(x->nplanes, (pl_maxpool2_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, C, xc_off, yc_off, total)));
+  NS_DISPATCH(x->nplanes, launch_k(pl_maxpool2_kernel<NS>, cdiv(total, 256), 256, 0, (cudaStream_t)stream, vx, vy, C, xc_off, yc_off, total));
   return check_launch("pl_maxpool2_kernel");
 }
 
@@ -303,13 +377,20 @@ extern "C" int sgta_planes_upsample_add(const sgta_planes* x, const void* w_up, 
   View vx = make_view(x), vy = make_view(y), vs = make_view(skip);
   const size_t smem = sizeof(float) * 4 * f * f * C;
   SGTA_REQUIRE(smem <= 96 * 1024 && y->B <= 65535, "sgta_planes_upsample_add: kernel %dx%d x %d channels too large", 2 * f, 2 * f, C);
+  if (f == 2 && !(debug_flags() & 65536)) {
+    dim3 grid2(cdiv((long long)(x->W + 1) * (C / 8), 256), cdiv(x->H + 1, UP2_ROWS), y->B);
+    NS_DISPATCH(x->nplanes, {
+      launch_k(pl_upsample2_add_kernel<NS>, grid2, 256, sizeof(float) * 16 * C, (cudaStream_t)stream, vx, (const float*)w_up, vs, (int)(skip != nullptr), vy, C);
+    });
+    return check_launch("pl_upsample2_add_kernel");
+  }
   int gx = cdiv((long long)y->W * (C / 8), 256);
   if (gx > 8) gx = 8;
   dim3 grid(gx, cdiv(y->H, UPS_ROWS), y->B);
   NS_DISPATCH(x->nplanes, {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(pl_upsample_add_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pl_upsample_add_kernel<NS><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, (const float*)w_up, vs, skip != nullptr, vy, C, f);
+    launch_k(pl_upsample_add_kernel<NS>, grid, 256, smem, (cudaStream_t)stream, vx, (const float*)w_up, vs, (int)(skip != nullptr), vy, C, f);
   });
   return check_launch("pl_upsample_add_kernel");
 }
@@ -320,8 +401,8 @@ extern "C" int sgta_planes_gather_tokens(const sgta_planes* x, int b_off, const 
                chan_ok(x, 0, C), "sgta_planes_gather_tokens: bad arguments");
   const long long total = (long long)B * n * (C / 8);
   View v = make_view(x);
-  NS_DISPATCH(x->nplanes, (pl_gather_tokens_kernel<NS><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                              v, b_off, (const long long*)ids, (float*)rows, C, n, total)));
+  NS_DISPATCH(x->nplanes, launch_k(pl_gather_tokens_kernel<NS>, cdiv(total, 256), 256, 0, (cudaStream_t)stream,
+                                   v, b_off, (const long long*)ids, (float*)rows, C, n, total));
   return check_launch("pl_gather_tokens_kernel");
 }
 
@@ -334,7 +415,7 @@ extern "C" int sgta_planes_scatter_tokens(const sgta_planes* x, int b_off, const
   NS_DISPATCH(x->nplanes, {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(pl_scatter_tokens_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pl_scatter_tokens_kernel<NS><<<dim3(B, cdiv(n, 96)), 256, smem, (cudaStream_t)stream>>>(v, b_off, (const long long*)ids, (const float*)rows, C, n);
+    launch_k(pl_scatter_tokens_kernel<NS>, dim3(B, cdiv(n, 96)), 256, smem, (cudaStream_t)stream, v, b_off, (const long long*)ids, (const float*)rows, C, n);
   });
   return check_launch("pl_scatter_tokens_kernel");
 }

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) token_linear_kernel(const
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tx = tid % (BN / 4), ty = tid / (BN / 4);
   const int K = p.K1 + p.K2;
@@ -130,9 +132,9 @@ int launch_token_linear(TokenLinearP& p, cudaStream_t st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   if ((long long)cdiv(M, 64) * cdiv(N, 64) >= sms) {
-    token_linear_kernel<64, 64><<<dim3(cdiv(N, 64), cdiv(M, 64)), 256, 0, st>>>(p);
+    launch_k(token_linear_kernel<64, 64>, dim3(cdiv(N, 64), cdiv(M, 64)), 256, 0, st, p);
   } else {
-    token_linear_kernel<32, 32><<<dim3(cdiv(N, 32), cdiv(M, 32)), 64, 0, st>>>(p);
+    launch_k(token_linear_kernel<32, 32>, dim3(cdiv(N, 32), cdiv(M, 32)), 64, 0, st, p);
   }
   return check_launch("token_linear_kernel");
 }

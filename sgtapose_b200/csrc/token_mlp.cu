@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(TmThreads<C>::value, 1) token_mlp_kernel(const
   const int tt = live ? t : p.T - 1;
 
   // ---- q1 = LN1(fc(att) + q): lane `sub` takes inputs k = sub, sub + LPT, ...
-  stage_rows<C>(sA, p.fc_w, p.hid, tid);                       // fc_w^T [hid][C] -> [hid][CS]
+  pdl_trigger();
+  stage_rows<C>(sA, p.fc_w, p.hid, tid);                       // fc_w^T [hid][C] -> [hid][CS]  (weights: before the wait)
+  pdl_wait();
   __syncthreads();
   float x[C];
 #pragma unroll
@@ -202,7 +204,7 @@ static int launch_token_mlp2(TokenMlpP& p, cudaStream_t st, int sms) {
   const size_t smem = sizeof(float) * ((size_t)(p.hid > jh ? p.hid : jh) * CS + (size_t)jh * CS);
   SGTA_REQUIRE(smem <= 220 * 1024, "sgta_token_mlp: weights do not fit shared memory");
   cudaFuncSetAttribute(token_mlp_kernel<C, LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  token_mlp_kernel<C, LPT><<<cdiv(p.T, TM_THREADS / LPT), TM_THREADS, smem, st>>>(p);
+  launch_k(token_mlp_kernel<C, LPT>, cdiv(p.T, TM_THREADS / LPT), TM_THREADS, smem, st, p);
   return check_launch("token_mlp_kernel");
 }
 

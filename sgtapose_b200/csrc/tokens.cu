@@ -18,6 +18,8 @@ topk_index_kernel(const float* __restrict__ hm, long long* __restrict__ idx, int
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   __shared__ int s_taken[64];
+  pdl_trigger();
+  pdl_wait();
   const float* src = hm + (long long)blockIdx.x * HW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = 0; r < K; ++r) {
@@ -56,6 +58,8 @@ topk_index_kernel(const float* __restrict__ hm, long long* __restrict__ idx, int
 // reference's x-major meshgrid, dla.py:932-942).  fp32 arithmetic without FMA contraction.
 __global__ void window_ids_kernel(const long long* __restrict__ idx, long long* __restrict__ ids,
                                   int total, int win, int Whm, float scale, int half, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   int win2 = win * win;
@@ -117,7 +121,7 @@ using namespace sgta;
 extern "C" int sgta_topk_index(const void* hm, void* idx, int B, int C, int HW, int K, void* stream) {
   SGTA_REQUIRE(hm && idx, "sgta_topk_index: null pointer");
   SGTA_REQUIRE(B > 0 && C > 0 && HW > 0 && K > 0 && K <= 64 && K <= HW, "sgta_topk_index: bad shape (K <= 64)");
-  topk_index_kernel<<<B * C, 256, 0, (cudaStream_t)stream>>>((const float*)hm, (long long*)idx, HW, K);
+  launch_k(topk_index_kernel, B * C, 256, 0, (cudaStream_t)stream, (const float*)hm, (long long*)idx, HW, K);
   return check_launch("topk_index_kernel");
 }
 
@@ -128,8 +132,8 @@ extern "C" int sgta_window_ids(const void* idx, void* ids, int B, int CK, int Wh
   int half = kernel / 2, win = 2 * half + 1;
   long long total = (long long)B * CK * win * win;
   SGTA_REQUIRE(total < (1ll << 31), "sgta_window_ids: too many tokens");
-  window_ids_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const long long*)idx, (long long*)ids, (int)total, win, Whm, scale, half, H, W);
+  launch_k(window_ids_kernel, cdiv(total, 256), 256, 0, (cudaStream_t)stream,
+           (const long long*)idx, (long long*)ids, (int)total, win, Whm, scale, half, H, W);
   return check_launch("window_ids_kernel");
 }
 

@@ -314,6 +314,15 @@ def test_planes_upsample_and_tokens(ns):
         yb = P.PlaneBuf(B, Cc, H * f, H * f, ns, DEV)
         P.upsample_add(xb.full, w.to(DEV), sb.full, yb.full, Cc, f)
         assert rel_err(yb.to_nchw().cpu(), ref) < (4e-3 if ns == 1 else 1e-6)
+        if f == 2:          # the four-outputs-per-thread kernel == the general kernel (debug flag 65536), bit for bit
+            from sgtapose_b200 import _lib
+            y2 = P.PlaneBuf(B, Cc, H * f, H * f, ns, DEV)
+            old_flags = _lib.load().sgta_debug_flags(65536)
+            try:
+                P.upsample_add(xb.full, w.to(DEV), sb.full, y2.full, Cc, f)
+            finally:
+                _lib.load().sgta_debug_flags(old_flags)
+            assert torch.equal(yb.t, y2.t)
     # tokens: gather from the second batch half, deterministic write-back with duplicates
     big = P.PlaneBuf(2 * B, Cc, H, H, ns, DEV)
     big.view(B, B).from_nchw(x.to(DEV))

@@ -1,7 +1,7 @@
 # round-2 check N: shift kernel roles as warpgroups (setmaxnreg) + scale / shift staged in shared memory for the fp32 epilogue
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_planes.py tests/test_gpu_ops.py -m gpu -x -q -k "planes or conv or engine_golden or superpixel or dcn" > gpurun_out/t_n.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/t_n.log
-timeout 300 python tools/wide_bench.py 0 2>&1 | tail -16
+timeout 300 python tools/wide_bench.py 0 32768 2>&1 | tail -16
 timeout 300 python tools/conv_bench.py 2 2>&1 | tail -6
 for dbg in 0; do
 timeout -k 5 200 python bench.py --dbg $dbg --no-cpu-baseline --no-extras 2>gpurun_out/bench_n.err | tee gpurun_out/bench_n_$dbg.json | python -c "
