@@ -374,6 +374,24 @@ __device__ __forceinline__ void stem_pixel(const ConvP& p, const float (&fa)[16]
   }
 }
 
+// the same with the 32 scale / shift values read from their shared-memory staging (fp32_epilogue_loop)
+__device__ __forceinline__ void stem_pixel_ss(uint32_t ss, const float (&fa)[16], const float (&fb)[16], float (&o16)[16]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const uint4 sa = lds128(ss + 16u * j4), sb = lds128(ss + 64u + 16u * j4);
+    const uint4 ha = lds128(ss + 512u + 16u * j4), hb = lds128(ss + 576u + 16u * j4);
+    const uint32_t s_a[4] = {sa.x, sa.y, sa.z, sa.w}, s_b[4] = {sb.x, sb.y, sb.z, sb.w};
+    const uint32_t h_a[4] = {ha.x, ha.y, ha.z, ha.w}, h_b[4] = {hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = 4 * j4 + i;
+      const float va = fmaf(fa[j], __uint_as_float(s_a[i]), __uint_as_float(h_a[i]));
+      const float vb = fmaf(fb[j], __uint_as_float(s_b[i]), __uint_as_float(h_b[i]));
+      o16[j] = fmaxf(va, 0.f) + fmaxf(vb, 0.f);
+    }
+  }
+}
+
 // scale / shift / residual / activation / store of 16 columns held in registers
 // SS: scale[16] at shared-memory address ss, shift[16] at ss + 512 (staged by fp32_epilogue_loop)
 template <int NS, bool SS = false>
@@ -499,16 +517,17 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
   // scale / shift of the N tile staged in shared memory by the epilogue warps themselves (one element per thread, two
   // buffers): read per 16-column group from global memory at the end of a tile they were L1 misses under the TMA
   // traffic -- half of the epilogue warps' stall samples on the 64 -> 768 head convolution
-  const bool stage_ss = p.epi != SGTA_EPI_STEM && p.epi != SGTA_EPI_STEM_SP;
+  const bool is_stem = p.epi == SGTA_EPI_STEM || p.epi == SGTA_EPI_STEM_SP;
+  const int ss_n = is_stem ? 32 : NT;                 // the dual stem has 32 scale / shift values whatever its N
   int ss_nt = -1;
   uint32_t ss_buf = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-    if (stage_ss && nt != ss_nt) {
+    if (nt != ss_nt) {
       ss_nt = nt;
       ss_buf ^= 1u;
       const int et = (half * 4 + q) * 32 + lane;
-      if (et < NT) {
+      if (et < ss_n) {
         epi_ss[ss_buf * 256 + et] = __ldg(p.scale + nt * NT + et);
         epi_ss[ss_buf * 256 + 128 + et] = __ldg(p.shift + nt * NT + et);
       }
@@ -612,11 +631,8 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
 #pragma unroll
         for (int j = 0; j < NG / 2; ++j) {
           if (j * 32 < NT) {
-            float lo8[8], hi8[8];
-            stem_pixel(p, acc[NG >= 2 ? 2 * j : 0], acc[NG >= 2 ? 2 * j + 1 : 0], lo8, hi8);
             float o16[16];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { o16[c] = lo8[c]; o16[8 + c] = hi8[c]; }
+            stem_pixel_ss(ss, acc[NG >= 2 ? 2 * j : 0], acc[NG >= 2 ? 2 * j + 1 : 0], o16);
             if (p.epi == SGTA_EPI_STEM) sc_store16<2>(p.y, e.m, 0, o16);
             else pl_store16<2>(p.y, 0, e.m, 2 * j, o16);
           }

@@ -14,6 +14,9 @@
 // produced and consumed one at a time, the weights are staged in shared memory in chunks of JH hidden
 // units ([JH][C] rows of W1 and of W2^T, read back as warp-broadcast LDS.128).
 // fp32 FMA throughout (the library path is SIMT fp32 too: TF32 is off for parity).
+// Measured and rejected (round 2): two tokens per lane group at C = 16 with twice the lanes per token (every weight row
+// read from shared memory feeds two tokens: half the LDS per token, same single wave of CTAs) -- 0.865 vs 0.840 ms
+// over the nine launches of a step: the kernel is bound by the dependent FFMA2 chains per hidden unit, not by LDS.
 #include "common.cuh"
 
 namespace sgta {
