@@ -53,8 +53,8 @@ constexpr int S_EPI_NH = 2;
 // of the first two groups to the epilogue warps (setmaxnreg): at 128 registers the band-drain epilogue spilled
 constexpr int S_W_MMA = S_TMA_WARPS, S_W_EPI = 8;
 constexpr int S_THREADS = (S_W_EPI + 4 * S_EPI_NH) * 32;
-// per-tile staging of the epilogue's scale / shift rows in shared memory: 2 buffers x [scale | shift] x 128 columns
-constexpr int EPI_SS_BYTES = 2 * 2 * 128 * 4;
+// per-tile staging of the epilogue's scale / shift rows in shared memory: 2 buffers x [scale | shift] x 256 columns
+constexpr int EPI_SS_BYTES = 2 * 2 * 256 * 4;
 constexpr int S_MAX_SB = 24;                             // B ring slots (resident weights: one per K block)
 
 enum { PROD_DCN = 0, PROD_STRIDE = 1, PROD_SMALLC = 2 };
@@ -379,7 +379,7 @@ __device__ __forceinline__ void stem_pixel_ss(uint32_t ss, const float (&fa)[16]
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     const uint4 sa = lds128(ss + 16u * j4), sb = lds128(ss + 64u + 16u * j4);
-    const uint4 ha = lds128(ss + 512u + 16u * j4), hb = lds128(ss + 576u + 16u * j4);
+    const uint4 ha = lds128(ss + 1024u + 16u * j4), hb = lds128(ss + 1088u + 16u * j4);
     const uint32_t s_a[4] = {sa.x, sa.y, sa.z, sa.w}, s_b[4] = {sb.x, sb.y, sb.z, sb.w};
     const uint32_t h_a[4] = {ha.x, ha.y, ha.z, ha.w}, h_b[4] = {hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
@@ -393,7 +393,7 @@ __device__ __forceinline__ void stem_pixel_ss(uint32_t ss, const float (&fa)[16]
 }
 
 // scale / shift / residual / activation / store of 16 columns held in registers
-// SS: scale[16] at shared-memory address ss, shift[16] at ss + 512 (staged by fp32_epilogue_loop)
+// SS: scale[16] at shared-memory address ss, shift[16] at ss + 1024 (staged by epi_stage_ss)
 template <int NS, bool SS = false>
 __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int n, float (&o)[16], uint32_t ss = 0u) {
   uint4 rv[2][NS];
@@ -410,7 +410,7 @@ __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int 
   for (int j = 0; j < 4; ++j) {
     float4 a, b4;
     if constexpr (SS) {
-      const uint4 ua = lds128(ss + 16u * j), ub = lds128(ss + 512u + 16u * j);
+      const uint4 ua = lds128(ss + 16u * j), ub = lds128(ss + 1024u + 16u * j);
       a = make_float4(__uint_as_float(ua.x), __uint_as_float(ua.y), __uint_as_float(ua.z), __uint_as_float(ua.w));
       b4 = make_float4(__uint_as_float(ub.x), __uint_as_float(ub.y), __uint_as_float(ub.z), __uint_as_float(ub.w));
     } else {
@@ -483,10 +483,10 @@ __device__ __forceinline__ void epi_finish(const ConvP& p, const EpiRow& e, int 
 }
 
 template <int NS>
-__device__ __forceinline__ void epilogue_group(const ConvP& p, const EpiRow& e, uint32_t tacc, int c0, int n) {
+__device__ __forceinline__ void epilogue_group(const ConvP& p, const EpiRow& e, uint32_t tacc, int c0, int n, uint32_t ss) {
   float o[16];
   epi_read<NS>(p, tacc, c0, o);
-  epi_finish<NS>(p, e, n, o);
+  epi_finish<NS, true>(p, e, n, o, ss + (uint32_t)c0 * 4u);
 }
 
 // ---- fp32 band-drain epilogue (see issue_kblock_f32): one thread = one output row (TMEM lane) and NG 16-column
@@ -506,6 +506,25 @@ __device__ __forceinline__ void epi_row_setup(const ConvP& p, int m, EpiRow& e) 
   e.staged = false;
   e.srow = 0; e.sxor = 0;
 }
+// scale / shift of the N tile staged in shared memory by the epilogue warps themselves (two buffers, refreshed when the
+// N tile changes): read per 16-column group from global memory at the end of a tile they were L1 misses under the TMA
+// traffic -- half of the epilogue warps' stall samples on the 64 -> 768 head convolution.  et = index of the calling
+// thread among the NH * 128 epilogue threads, which all call this once per tile.  Returns the buffer's address.
+template <int NH>
+__device__ __forceinline__ uint32_t epi_stage_ss(const ConvP& p, int nt, int& ss_nt, uint32_t& ss_buf, float* epi_ss, int et) {
+  if (nt != ss_nt) {
+    ss_nt = nt;
+    ss_buf ^= 1u;
+    const bool is_stem = p.epi == SGTA_EPI_STEM || p.epi == SGTA_EPI_STEM_SP;
+    const int ss_n = is_stem ? 32 : p.NT;               // the dual stem has 32 scale / shift values whatever its N
+    for (int c = et; c < ss_n; c += NH * 128) {
+      epi_ss[ss_buf * 512 + c] = __ldg(p.scale + nt * p.NT + c);
+      epi_ss[ss_buf * 512 + 256 + c] = __ldg(p.shift + nt * p.NT + c);
+    }
+    asm volatile("bar.sync 3, %0;" ::"n"(NH * 128) : "memory");
+  }
+  return smem_u32(epi_ss) + ss_buf * 2048u;
+}
 template <int NG, int NH, bool BACKOFF>
 __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem, int total, int nbands, int q, int half,
                                                    int lane, uint64_t* slot_full, uint64_t* slot_empty, uint64_t* d1_empty,
@@ -514,26 +533,11 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
   const bool wide = p.wide != 0;
   const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
   Ring rs{0u, 0u, p.nslots}, rd{0u, 0u, p.nd1};
-  // scale / shift of the N tile staged in shared memory by the epilogue warps themselves (one element per thread, two
-  // buffers): read per 16-column group from global memory at the end of a tile they were L1 misses under the TMA
-  // traffic -- half of the epilogue warps' stall samples on the 64 -> 768 head convolution
-  const bool is_stem = p.epi == SGTA_EPI_STEM || p.epi == SGTA_EPI_STEM_SP;
-  const int ss_n = is_stem ? 32 : NT;                 // the dual stem has 32 scale / shift values whatever its N
   int ss_nt = -1;
   uint32_t ss_buf = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
-    if (nt != ss_nt) {
-      ss_nt = nt;
-      ss_buf ^= 1u;
-      const int et = (half * 4 + q) * 32 + lane;
-      if (et < ss_n) {
-        epi_ss[ss_buf * 256 + et] = __ldg(p.scale + nt * NT + et);
-        epi_ss[ss_buf * 256 + 128 + et] = __ldg(p.shift + nt * NT + et);
-      }
-      asm volatile("bar.sync 3, %0;" ::"n"(NH * 128) : "memory");
-    }
-    const uint32_t ss = smem_u32(epi_ss) + ss_buf * 1024u;
+    const uint32_t ss = epi_stage_ss<NH>(p, nt, ss_nt, ss_buf, epi_ss, (half * 4 + q) * 32 + lane);
     float acc[NG][16];
     float acc1[NG <= 2 ? NG : 1][16];                 // wide form, NG <= 2: the D1 halves of the band slots
 #pragma unroll
@@ -658,7 +662,7 @@ __device__ __forceinline__ void fp32_epilogue(const ConvP& p, uint32_t tmem, int
 // NH epilogue warps per lane quadrant; `half` in [0, NH) is this warp's share
 template <int NS, int NH>
 __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int m0, int n0, int row, uint32_t stage_s,
-                                              int half, uint64_t* release, int m_abs = -1) {
+                                              int half, uint64_t* release, uint32_t ss, int m_abs = -1) {
   const int NT = p.NT;
   EpiRow e;
   e.m = m_abs >= 0 ? m_abs : m0 + row;
@@ -693,22 +697,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int
   e.staged = stage_s != 0 && p.epi == SGTA_EPI_PL && m0 + TM <= p.P;
   e.srow = stage_s + (uint32_t)row * 128u;
   e.sxor = (uint32_t)((p.y.guard + e.m) & 7);
-  if (NS == 2 && NH == 1 && release != nullptr && NT == 128 && !e.staged) {
-    // single accumulator stage (fp32 mode, 128-wide tile): drain the whole row into registers, hand
-    // TMEM back to the MMA warp, THEN do the math and the stores -- they overlap the next tile's MMAs
-    float o[8][16];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      __syncwarp();
-      read_acc16<NS>(tacc, NT, p.acc_r, g * 16, o[g]);       // one 16-register buffer: o[8][16] is the budget
-    }
-    tc_fence_before();
-    __syncwarp();
-    if ((row & 31) == 0) mbar_arrive(release);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) epi_finish<NS>(p, e, n0 + g * 16, o[g]);
-    return;
-  }
   const int G = (NT < 64 ? NT : 64) >> 4;              // 16-column groups per chunk: 1, 2 or 4
   const bool leader = row == 0 && half == 0;
   for (int c0 = 0; c0 < NT; c0 += 16) {
@@ -720,7 +708,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvP& p, uint32_t tacc, int
     }
     const int gi = (c0 >> 4) & (G - 1);
     const bool mine = NH == 1 || (G == 1 ? half == 0 : (gi * NH) / G == half);
-    if (mine) epilogue_group<NS>(p, e, tacc, c0, n);
+    if (mine) epilogue_group<NS>(p, e, tacc, c0, n, ss);
     if (e.staged && (c0 & 63) == 48) {
       fence_async_smem();
       epi_bar<NH>();
@@ -939,14 +927,16 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
       const int per = BAND_KSTEPS / (SPK ? 6 : ntap_b * 4);     // ... per D0 band: 1 (3x3), 3 (1x1) or 2 (super-pixel 3x3)
       fp32_epilogue<S_EPI_NH, false>(p, tmem, total, (steps + per - 1) / per, q, half, lane, slot_full, slot_empty, acc_empty, epi_ss);
     } else {
-      uint32_t as = 0, accph = 0;
+      uint32_t as = 0, accph = 0, ss_buf = 0;
+      int ss_nt = -1;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+        const uint32_t ss = epi_stage_ss<S_EPI_NH>(p, nt, ss_nt, ss_buf, epi_ss, (half * 4 + q) * 32 + lane);
         mbar_wait_backoff(&acc_full[as], accph);
         tc_fence_after();
         if (!(p.dbg & 4))
           epilogue_tile<NS, S_EPI_NH>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
-                                      p.stg_bytes ? smem_u32(smem) : 0u, half, nullptr);
+                                      p.stg_bytes ? smem_u32(smem) : 0u, half, nullptr, ss);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -1366,14 +1356,16 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
       fp32_epilogue<1, true, (WIDE || PROD != PROD_DCN) ? 8 : 4>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane,
                                                                   slot_full, slot_empty, acc_empty, epi_ss);
     } else {
-      uint32_t as = 0, accph = 0;
+      uint32_t as = 0, accph = 0, ss_buf = 0;
+      int ss_nt = -1;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+        const uint32_t ss = epi_stage_ss<1>(p, nt, ss_nt, ss_buf, epi_ss, q * 32 + lane);
         mbar_wait_backoff(&acc_full[as], accph);
         tc_fence_after();
         if (!(p.dbg & 4))
           epilogue_tile<NS, 1>(p, tmem + as * acc_stride + ((uint32_t)(q * 32) << 16), m0, nt * NT, q * 32 + lane,
-                               p.stg_bytes ? smem_u32(smem) : 0u, 0, nullptr);
+                               p.stg_bytes ? smem_u32(smem) : 0u, 0, nullptr, ss);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -1628,12 +1620,14 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
       constexpr int BAND_KB = BAND_KSTEPS / 4;
       fp32_epilogue<1, true, WIDE ? 8 : 4>(p, tmem, total, (nkb + BAND_KB - 1) / BAND_KB, q, 0, lane, slot_full, slot_empty, acc_empty, epi_ss);
     } else {
-      uint32_t as = 0, accph = 0;
+      uint32_t as = 0, accph = 0, ss_buf = 0;
+      int ss_nt = -1;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const uint32_t ss = epi_stage_ss<1>(p, 0, ss_nt, ss_buf, epi_ss, q * 32 + lane);      // n_tiles == 1
         mbar_wait_backoff(&acc_full[as], accph);
         tc_fence_after();
         if (!(p.dbg & 4))
-          epilogue_tile<NS, 1>(p, tmem + as * (uint32_t)NT + ((uint32_t)(q * 32) << 16), 0, 0, q * 32 + lane, 0u, 0, nullptr,
+          epilogue_tile<NS, 1>(p, tmem + as * (uint32_t)NT + ((uint32_t)(q * 32) << 16), 0, 0, q * 32 + lane, 0u, 0, nullptr, ss,
                                tile_row_m(p, t, q * 32 + lane));
         tc_fence_before();
         __syncwarp();
