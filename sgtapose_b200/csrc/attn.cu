@@ -303,6 +303,10 @@ attn_fwd_batched_kernel(const float* __restrict__ q, const float* __restrict__ k
 // KVHM: K / V are given head-major, [B, heads, nk, D] (sgta_token_linear_heads writes them that way): the slab of a
 // (sample, head) is contiguous, so the per-sample prefetch is coalesced 16-byte loads instead of one 16-byte piece per
 // 128-byte line ("b n (h d)": a third of this kernel's stall samples were LSU-queue throttling on those gathers).
+// Measured and rejected (round 2, 0.985 ms per step for the three level-0 launches): K / V transposed in shared memory
+// with the scores and P V as FFMA2 on key pairs (a third fewer instructions per key: 0.984 ms, no change -- the inner
+// loop is ~2 us of the ~5 us a CTA spends per sample; the rest is the three barriers, the staging and the merge);
+// merging the 16 slices with all 512 threads and xor-shuffles (1.035 ms with a conflict-free layout, 1.185 without).
 template <int D, bool KVHM>
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_fwd_rows_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
