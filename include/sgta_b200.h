@@ -106,6 +106,7 @@ typedef struct sgta_planes {
  * image row; a 16-channel map [B,H,W] is then a 64-channel PL view [B,H,W/4] (channel j*16 + c = pixel j, channel c) */
 #define SGTA_EPI_STEM_SP 5  /* Cout == 128 = 4 px x (16+16): the dual-stem epilogue per pixel -> 64-channel PL view      */
 #define SGTA_EPI_SP2SC 6    /* Cout == 64 = 4 px x 16 ch -> 16-channel SC view [B,H,4*W]: pixel j of row (y,X) -> (y,4X+j) */
+#define SGTA_EPI_HEADS 7    /* internal to sgta_planes_conv_heads: fused 1x1 output convolutions, fp32 NCHW outputs            */
 /* A 3x3 convolution with EPI_SP2SC and Cin == 64 is taken to be a 16 -> 16 convolution over super-pixels: its weight
  * matrix MUST be the Toeplitz expansion planes.superpixel_weight(w, 4, 4, 1) -- the left / right neighbour taps are
  * zero except for their last / first pixel, and the kernel does not issue those all-zero K steps. */
@@ -129,6 +130,17 @@ int sgta_planes_conv(const sgta_planes* x, const void* wpack, const void* scale,
                      const sgta_planes* res, const sgta_planes* y, void* y_f32, int64_t ld_f32,
                      int Cin, int Cout, int ksize, int stride, int act, int epi, int n_valid,
                      void* stream);
+/* The head stack of the network in ONE launch (base_model.py:121-135 build, :190-199 call): for every head h
+ *   out[h] = act_h( W2_h * relu(scale * conv3x3(x)[h*hid .. (h+1)*hid) + shift) + b2_h )     fp32 [B, nout[h], H, W]
+ * -- the 3x3 convolutions of all heads as one Cin -> n_heads*hid shift-GEMM (wpack / scale / shift as for
+ * sgta_planes_conv) with the 1x1 output convolutions folded into its epilogue in fp32 FMA arithmetic; the hidden map is
+ * never written.  fp32 mode (2 planes) only; hid must be a multiple of the kernel's N tile (128); nout[h] <= 8.
+ * w2: device fp32, per head [hid][stride_h] with stride_h = 2 / 4 / 8 for nout <= 2 / 4 / 8 (row k = the nout weights of
+ * hidden channel k, zero padded), heads back to back; b2: device fp32 [n_heads][8]; out / nout: HOST arrays [n_heads];
+ * bit h of sigmoid_mask applies the detector's sigmoid (sgta_detector.py:854-862) to head h. */
+int sgta_planes_conv_heads(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
+                           const void* w2, const void* b2, void* const* out, const int* nout, int n_heads,
+                           int sigmoid_mask, int Cin, int hid, void* stream);
 /* Convolution on an SC input (stems dla.py:241-270, level0/1 :302-312, level2 entry).  K block
  * kb (64 wide = 128 bytes per output pixel) is made of 8/seg_groups segments; segment j is a
  * run of seg_groups*16 contiguous bytes starting at input row

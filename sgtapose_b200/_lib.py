@@ -36,6 +36,7 @@ SIGNATURES = {
     "sgta_planes_wpack_bytes": (_c.c_int64, [_I, _I, _I]),
     "sgta_planes_pack_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "sgta_planes_conv": (_I, [_V, _P, _P, _P, _V, _V, _P, _L] + [_I] * 7 + [_P]),
+    "sgta_planes_conv_heads": (_I, [_V, _P, _P, _P, _P, _P, _c.POINTER(_P), _c.POINTER(_I), _I, _I, _I, _I, _P]),
     "sgta_planes_conv_sc": (_I, [_V, _P, _P, _P, _V] + [_I] * 7 + [_c.POINTER(_I), _I, _I, _P]),
     "sgta_planes_dcn": (_I, [_V, _P, _P, _P, _P, _V, _I, _I, _I, _P]),
     "sgta_planes_from_nchw": (_I, [_P, _V, _I, _I, _P]),

@@ -89,6 +89,15 @@ struct ConvP {
   unsigned long long magic_wp, magic_hp;   // ceil(2^64 / (Wo+2)), ceil(2^64 / (Ho+2)): exact m / d for m < 2^32
   int b_resident;        // gather kernels: all weight blocks stay in shared memory (n_tiles == 1)
   int stg_bytes;         // EPI_PL: bytes of the epilogue's store staging tile (one 64-channel chunk x planes) at the head of smem
+  // EPI_HEADS (fp32 mode): the 1x1 output convolutions of the heads fused into the epilogue of the 64 -> 3 x 256 head
+  // convolution (base_model.py:121-135, :190-199).  Tiles are walked M-major (one CTA takes all N tiles of an M tile),
+  // head h = h_tiles consecutive N tiles; w2: per head [hid][w2_stride[h]] fp32 (row k = the output weights of hidden
+  // channel k, zero padded), heads back to back at w2_off[h] floats; b2 [n_heads][8]; out2[h]: fp32 [B, nout[h], Ho, Wo]
+  int m_major, n_heads, h_tiles, sig_mask, w2_floats, heads_bytes;
+  const float* w2;
+  const float* b2;
+  float* out2[4];
+  int nout[4], w2_off[4], w2_stride[4];
   int dbg;               // tools/conv_bench.py: 1 = skip A copies, 2 = skip B copies, 4 = skip epilogue math
   // dcn_tile_kernel: output tiles of 8 x 16 pixels; the input tile + halo is staged in shared memory
   int tile2d, tiles_x, tiles_y, halo, LW, LH, xt_plane;
@@ -111,6 +120,22 @@ __device__ __forceinline__ void decode_row(const ConvP& p, int m, int& px, int& 
   px = m - (int)t * (p.Wo + 2);
   b = (int)__umul64hi((unsigned long long)t, p.magic_hp);
   py = (int)t - b * (p.Ho + 2);
+}
+// tile `it` of this CTA: N-major round-robin over all `total` tiles (the caller's count: dcn_tile_kernel walks 2-D
+// tiles, not p.m_tiles), or (m_major) all N tiles of M tile blockIdx.x + q * gridDim.x
+__device__ __forceinline__ bool tile_at(const ConvP& p, int total, int it, int& nt, int& m0, int& t) {
+  if (p.m_major) {
+    const int q = it / p.n_tiles;
+    nt = it - q * p.n_tiles;
+    const int mt = (int)blockIdx.x + q * (int)gridDim.x;
+    m0 = mt * TM;
+    t = mt * p.n_tiles + nt;
+    return mt < p.m_tiles;
+  }
+  t = (int)blockIdx.x + it * (int)gridDim.x;
+  nt = t % p.n_tiles;
+  m0 = (t / p.n_tiles) * TM;
+  return t < total;
 }
 static unsigned long long magic_u64(unsigned d) { return d <= 1 ? ~0ull : (~0ull / d) + 1; }
 
@@ -506,6 +531,86 @@ __device__ __forceinline__ void epi_row_setup(const ConvP& p, int m, EpiRow& e) 
   e.staged = false;
   e.srow = 0; e.sxor = 0;
 }
+// ---- EPI_HEADS: hidden = relu(scale * acc + shift) stays in registers; out[o] += hidden[k] * w2[k][o] over the thread's
+// columns of the N tile (fp32 FMA), accumulated over the h_tiles N tiles of a head (the CTA walks them back to back:
+// m_major); after the last one the NH column halves of a row meet through shared memory (two addends: order-free),
+// bias + optional sigmoid, fp32 NCHW store (lane = pixel: coalesced per output channel).  The 768-channel hidden map
+// never reaches HBM (it was 856 MB written + 945 MB read back per step of 32 frame pairs) and the three 1x1 launches go.
+template <int NG, int NH>
+__device__ __forceinline__ void heads_tile(const ConvP& p, int nt, int m0, int q, int half, int lane, int g0, uint32_t ss,
+                                           float (&acc)[NG][16], float (&h2)[8], float* w2s) {
+  const int hd = nt / p.h_tiles, sub = nt - hd * p.h_tiles;
+  const int stride = p.w2_stride[hd];
+  const uint32_t wbase = smem_u32(w2s + p.w2_off[hd]);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if ((g0 + g) * 16 >= p.NT) continue;
+    const uint32_t ssg = ss + (uint32_t)((g0 + g) * 64);
+    const int k0 = sub * p.NT + (g0 + g) * 16;                 // hidden channel of column 0 of this group, inside the head
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const uint4 ua = lds128(ssg + 16u * j4), ub = lds128(ssg + 1024u + 16u * j4);
+      const uint32_t sc4[4] = {ua.x, ua.y, ua.z, ua.w}, sh4[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 4 * j4 + i;
+        const float v = fmaxf(fmaf(acc[g][j], __uint_as_float(sc4[i]), __uint_as_float(sh4[i])), 0.f);
+        const uint32_t wa = wbase + (uint32_t)((k0 + j) * stride) * 4u;
+        if (stride == 8) {
+          const uint4 w0 = lds128(wa), w1 = lds128(wa + 16u);
+          h2[0] = fmaf(v, __uint_as_float(w0.x), h2[0]); h2[1] = fmaf(v, __uint_as_float(w0.y), h2[1]);
+          h2[2] = fmaf(v, __uint_as_float(w0.z), h2[2]); h2[3] = fmaf(v, __uint_as_float(w0.w), h2[3]);
+          h2[4] = fmaf(v, __uint_as_float(w1.x), h2[4]); h2[5] = fmaf(v, __uint_as_float(w1.y), h2[5]);
+          h2[6] = fmaf(v, __uint_as_float(w1.z), h2[6]); h2[7] = fmaf(v, __uint_as_float(w1.w), h2[7]);
+        } else if (stride == 4) {
+          const uint4 w0 = lds128(wa);
+          h2[0] = fmaf(v, __uint_as_float(w0.x), h2[0]); h2[1] = fmaf(v, __uint_as_float(w0.y), h2[1]);
+          h2[2] = fmaf(v, __uint_as_float(w0.z), h2[2]); h2[3] = fmaf(v, __uint_as_float(w0.w), h2[3]);
+        } else {
+          uint32_t wx, wy;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wx), "=r"(wy) : "r"(wa));
+          h2[0] = fmaf(v, __uint_as_float(wx), h2[0]); h2[1] = fmaf(v, __uint_as_float(wy), h2[1]);
+        }
+      }
+    }
+  }
+  if (sub != p.h_tiles - 1) return;
+  // last N tile of the head: the column halves of each row meet
+  const int row = q * 32 + lane;
+  float* xch = w2s + p.w2_floats + row * 8;
+  if (NH > 1 && half != 0) {
+    sts128(smem_u32(xch), make_uint4(__float_as_uint(h2[0]), __float_as_uint(h2[1]), __float_as_uint(h2[2]), __float_as_uint(h2[3])));
+    sts128(smem_u32(xch) + 16u, make_uint4(__float_as_uint(h2[4]), __float_as_uint(h2[5]), __float_as_uint(h2[6]), __float_as_uint(h2[7])));
+  }
+  if (NH > 1) asm volatile("bar.sync 3, %0;" ::"n"(NH * 128) : "memory");
+  if (half == 0) {
+    if (NH > 1) {
+      const uint4 x0 = lds128(smem_u32(xch)), x1 = lds128(smem_u32(xch) + 16u);
+      h2[0] += __uint_as_float(x0.x); h2[1] += __uint_as_float(x0.y); h2[2] += __uint_as_float(x0.z); h2[3] += __uint_as_float(x0.w);
+      h2[4] += __uint_as_float(x1.x); h2[5] += __uint_as_float(x1.y); h2[6] += __uint_as_float(x1.z); h2[7] += __uint_as_float(x1.w);
+    }
+    EpiRow e;
+    epi_row_setup(p, m0 + row, e);
+    if (e.valid) {
+      const int no = p.nout[hd];
+      const size_t hw = (size_t)p.Ho * p.Wo;
+      float* dst = p.out2[hd] + (size_t)e.b * no * hw + (size_t)(e.py - 1) * p.Wo + (e.px - 1);
+      const bool sig = (p.sig_mask >> hd) & 1;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        if (o < no) {
+          float v = h2[o] + __ldg(p.b2 + hd * 8 + o);
+          if (sig) v = 1.f / (1.f + expf(-v));
+          dst[(size_t)o * hw] = v;
+        }
+      }
+    }
+  }
+  if (NH > 1) asm volatile("bar.sync 3, %0;" ::"n"(NH * 128) : "memory");      // the exchange buffer is free again
+#pragma unroll
+  for (int o = 0; o < 8; ++o) h2[o] = 0.f;
+}
+
 // scale / shift of the N tile staged in shared memory by the epilogue warps themselves (two buffers, refreshed when the
 // N tile changes): read per 16-column group from global memory at the end of a tile they were L1 misses under the TMA
 // traffic -- half of the epilogue warps' stall samples on the 64 -> 768 head convolution.  et = index of the calling
@@ -535,8 +640,16 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
   Ring rs{0u, 0u, p.nslots}, rd{0u, 0u, p.nd1};
   int ss_nt = -1;
   uint32_t ss_buf = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x) {
-    const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+  // EPI_HEADS: the fused 1x1 weights sit behind the scale / shift staging, then the half-to-half exchange buffer
+  float h2[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) h2[o] = 0.f;
+  float* w2s = epi_ss + EPI_SS_BYTES / 4;
+  if (p.epi == SGTA_EPI_HEADS) {
+    for (int i = (half * 4 + q) * 32 + lane; i < p.w2_floats; i += NH * 128) w2s[i] = __ldg(p.w2 + i);
+    asm volatile("bar.sync 3, %0;" ::"n"(NH * 128) : "memory");
+  }
+  for (int it = 0, nt, m0, t; tile_at(p, total, it, nt, m0, t); ++it) {
     const uint32_t ss = epi_stage_ss<NH>(p, nt, ss_nt, ss_buf, epi_ss, (half * 4 + q) * 32 + lane);
     float acc[NG][16];
     float acc1[NG <= 2 ? NG : 1][16];                 // wide form, NG <= 2: the D1 halves of the band slots
@@ -626,6 +739,10 @@ __device__ __forceinline__ void fp32_epilogue_loop(const ConvP& p, uint32_t tmem
       rd.next();
     }
     if (p.dbg & (4 | 8192)) continue;                       // 8192: drain TMEM but skip the math and the stores
+    if (p.epi == SGTA_EPI_HEADS) {
+      if constexpr (NG <= 4) heads_tile<NG, NH>(p, nt, m0, q, half, lane, g0, ss, acc, h2, w2s);
+      continue;
+    }
     EpiRow e;
     epi_row_setup(p, p.tile2d ? tile_row_m(p, t / p.n_tiles, q * 32 + lane) : m0 + q * 32 + lane, e);
     if (p.epi == SGTA_EPI_STEM || p.epi == SGTA_EPI_STEM_SP) {
@@ -785,8 +902,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
       int st = 0, sb = 0;
       uint32_t aph = 1, bph = 1;           // parity to wait for on the *_empty barriers
       const bool skipA = p.dbg & 1, skipB = p.dbg & 2;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int nt = t % p.n_tiles, m0 = (t / p.n_tiles) * TM;
+      for (int it = 0, nt, m0, t; tile_at(p, total, it, nt, m0, t); ++it) {
         const unsigned char* wt = p.wpack + (size_t)nt * p.nkb * b_stage;
         for (int kc = 0; kc < p.KC; ++kc) {
           for (int band = 0; band < nb; ++band) {
@@ -807,7 +923,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
               if (((sb + 2) & (S_TMA_WARPS - 1)) == warp) {
                 mbar_wait(&b_empty[sb], bph);
                 // resident weights (SB == nkb): every slot is filled during this CTA's first tile and only re-armed later
-                if (skipB || (p.b_resident && t != (int)blockIdx.x)) mbar_arrive(&b_full[sb]);
+                if (skipB || (p.b_resident && it != 0)) mbar_arrive(&b_full[sb]);
                 else {
                   const int tap = band * ntap_b + dx;
                   mbar_arrive_expect_tx(&b_full[sb], b_stage);
@@ -831,8 +947,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_shift_kernel(const __grid_c
     uint32_t as = 0, accph = 1;            // accumulator stage and parity of its acc_empty barrier
     Ring rs{0u, 1u, p.nslots}, rd{0u, 1u, p.nd1};   // fp32 mode: D0 band slots / D1 buffers (parity of their *_empty)
     const uint32_t a_smem = smem_u32(sA), b_smem = smem_u32(sB);
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int m0 = (t / p.n_tiles) * TM;
+    for (int it = 0, nt_, m0, t_; tile_at(p, total, it, nt_, m0, t_); ++it) {
       uint32_t tacc = 0, tD0 = 0, tD1 = 0, sl = 0;
       if constexpr (NS == 2) {
         if (!p.wide) {
@@ -1805,7 +1920,7 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   p.b_resident = 0;
   if (p.n_tiles == 1 && p.nkb <= S_MAX_SB && p.nkb >= min_sb && !(p.dbg & 2048)) {
     const int stg = (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 16384 * NS : 0;
-    const int fx = 1024 + 1024 + EPI_SS_BYTES + stg;
+    const int fx = 1024 + 1024 + EPI_SS_BYTES + p.heads_bytes + stg;
     if (2 * a_stage + p.nkb * b_stage + fx <= SMEM_LIMIT) {
       p.b_resident = 1;
       p.stg_bytes = stg;
@@ -1818,7 +1933,7 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   // (fp32 mode: measured no gain -- the hi/lo tile needs 32 KB that the weight ring uses better)
   for (int with_stg = p.b_resident ? -1 : (NS == 1 && p.epi == SGTA_EPI_PL && !(p.dbg & 8)) ? 1 : 0; with_stg >= 0; --with_stg) {
     p.stg_bytes = with_stg ? 16384 * NS : 0;
-    fixed = 1024 + 1024 + EPI_SS_BYTES + p.stg_bytes;
+    fixed = 1024 + 1024 + EPI_SS_BYTES + p.heads_bytes + p.stg_bytes;
     SB = 4; SA = 3;
     while (SB > min_sb && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SB;
     while (SA > 1 && SA * a_stage + SB * b_stage + fixed > SMEM_LIMIT) --SA;
@@ -1835,7 +1950,7 @@ static int launch_shift(ConvP& p, cudaStream_t st) {
   const int smem = SA * a_stage + SB * b_stage + fixed;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_major ? p.m_tiles : p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
   if (p.spk) {
     cudaFuncSetAttribute(conv_shift_kernel<NS, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -2028,6 +2143,46 @@ extern "C" int sgta_planes_conv(const sgta_planes* x, const void* wpack, const v
   // SC input: K blocks described by the caller through sgta_planes_conv_sc
   set_error("sgta_planes_conv: SC inputs go through sgta_planes_conv_sc");
   return SGTA_EINVAL;
+}
+
+extern "C" int sgta_planes_conv_heads(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,
+                                      const void* w2, const void* b2, void* const* out, const int* nout, int n_heads,
+                                      int sigmoid_mask, int Cin, int hid, void* stream) {
+  SGTA_REQUIRE(x && wpack && scale && shift && w2 && b2 && out && nout, "sgta_planes_conv_heads: null pointer");
+  SGTA_REQUIRE(view_ok(x, SGTA_LAYOUT_PL) && x->border == 1 && x->nplanes == 2, "sgta_planes_conv_heads: fp32-mode PL input view expected");
+  SGTA_REQUIRE(n_heads >= 1 && n_heads <= 4 && Cin % 64 == 0 && x->chunk0 + Cin / 64 <= x->nchunks, "sgta_planes_conv_heads: bad shape");
+  const int NS = 2, Cout = n_heads * hid;
+  const int NT = pick_ntile(Cout, NS);
+  SGTA_REQUIRE(NT > 0 && hid % NT == 0, "sgta_planes_conv_heads: hid (%d) must be a multiple of the N tile (%d)", hid, NT);
+  ConvP p{};
+  p.dbg = g_dbg;
+  p.x = make_view(x);
+  p.wpack = (const unsigned char*)wpack; p.scale = (const float*)scale; p.shift = (const float*)shift;
+  p.act = SGTA_ACT_RELU; p.stride = 1; p.sx = 1; p.NT = NT; p.n_tiles = Cout / NT;
+  const long long P = (long long)x->B * (x->H + 2) * (x->W + 2);
+  SGTA_REQUIRE(P < (1ll << 31) - 2 * TM, "sgta_planes_conv_heads: too many pixels");
+  p.P = (int)P; p.Ho = x->H; p.Wo = x->W; p.m_tiles = cdiv(P, TM);
+  p.magic_wp = magic_u64(x->W + 2); p.magic_hp = magic_u64(x->H + 2);
+  p.epi = SGTA_EPI_HEADS; p.n_valid = Cout;
+  p.in_Wp = x->W + 2; p.in_Hp = x->H + 2;
+  p.KC = Cin / 64; p.taps = 9; p.nkb = 9 * p.KC; p.a_rows = 144;
+  p.m_major = 1; p.n_heads = n_heads; p.h_tiles = hid / NT; p.sig_mask = sigmoid_mask;
+  p.w2 = (const float*)w2; p.b2 = (const float*)b2;
+  int off = 0;
+  for (int h = 0; h < n_heads; ++h) {
+    SGTA_REQUIRE(out[h] && nout[h] >= 1 && nout[h] <= 8, "sgta_planes_conv_heads: head %d: bad output", h);
+    p.out2[h] = (float*)out[h]; p.nout[h] = nout[h];
+    p.w2_stride[h] = nout[h] <= 2 ? 2 : nout[h] <= 4 ? 4 : 8;
+    p.w2_off[h] = off;
+    off += hid * p.w2_stride[h];
+  }
+  p.w2_floats = off;
+  p.heads_bytes = off * 4 + TM * 8 * 4;                      // fused weights + the half-to-half exchange buffer
+  plan_acc(p, NS);
+  const int Wp = x->W + 2;
+  SGTA_REQUIRE(x->guard >= Wp + 1 + 8 && x->rows >= (int64_t)x->guard + (int64_t)p.m_tiles * TM + Wp + 16 + 8,
+               "sgta_planes_conv_heads: input guard rows too small for the halo");
+  return launch_shift<2>(p, (cudaStream_t)stream);
 }
 
 extern "C" int sgta_planes_conv_sc(const sgta_planes* x, const void* wpack, const void* scale, const void* shift,

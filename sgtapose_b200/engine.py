@@ -24,6 +24,8 @@ mode="fp32": fp32 activations as fp16 hi + lo planes, 3 tensor-core MMAs per K s
              accumulation (parity bound 1e-3 relative);
 mode="bf16": bf16 activations and MMAs, fp32 accumulate (stated looser bound).
 """
+import os
+
 import torch
 
 from . import decode, fusion
@@ -149,6 +151,13 @@ class InferenceEngine:
             act = P.ACT_SIGMOID if (h == "hm" and self.fuse_sigmoid) else P.ACT_NONE
             s["head2." + h] = P.ConvSpec(P.weight_matrix(w2), torch.ones_like(b2), b2, 256, 1, 1, self.ns, act,
                                          n_valid=w2.shape[0])
+        # fp32 mode: the 1x1 output convolutions ride in the epilogue of the stacked 3x3 head convolution (one launch,
+        # the 768-channel hidden map is never written); bf16 mode keeps the two-stage form
+        self.fused_heads = None
+        if self.ns == 2 and os.environ.get("SGTA_UNFUSED_HEADS") is None:
+            self.fused_heads = P.HeadsSpec([sd[h + ".2.weight"].float() for h in self.head_names],
+                                           [sd[h + ".2.bias"].float() for h in self.head_names],
+                                           [h == "hm" and self.fuse_sigmoid for h in self.head_names])
         self.specs = s
 
     # ------------------------------------------------------------------ buffers
@@ -340,9 +349,12 @@ class InferenceEngine:
         y1 = self._ida_step("ida_up", 1, b5, c5, 2)
         y2 = self._ida_step("ida_up", 2, a5, y1, 4)
         # heads
-        P.conv(s["head0"], y2, b["hid"].full)
-        for j, h in enumerate(self.head_names):
-            P.conv(s["head2." + h], b["hid"].view(c0=256 * j, C=256), y_f32=self.out[h], epi=P.EPI_NCHW)
+        if self.fused_heads is not None:
+            P.conv_heads(s["head0"], self.fused_heads, y2, [self.out[h] for h in self.head_names])
+        else:
+            P.conv(s["head0"], y2, b["hid"].full)
+            for j, h in enumerate(self.head_names):
+                P.conv(s["head2." + h], b["hid"].view(c0=256 * j, C=256), y_f32=self.out[h], epi=P.EPI_NCHW)
         self.feat_view = y2
 
     @property

@@ -239,6 +239,40 @@ class ScConvSpec:
         self.Cout, self.stride, self.ksize, self.pad, self.act = Cp, stride, ksize, pad, act
 
 
+class HeadsSpec:
+    """The 1x1 output convolutions of the heads, packed for sgta_planes_conv_heads (base_model.py:121-135): per head the
+    [nout, hid] weight as [hid][stride] fp32 rows (stride 2 / 4 / 8, zero padded), heads back to back; biases [n_heads][8]."""
+
+    def __init__(self, weights, biases, sigmoid):
+        """weights: list of [nout, hid(,1,1)] tensors; biases: list of [nout]; sigmoid: list of bool."""
+        dev = weights[0].device
+        self.hid = weights[0].reshape(weights[0].shape[0], -1).shape[1]
+        self.nout = [int(w.shape[0]) for w in weights]
+        parts = []
+        self.b2 = torch.zeros(len(weights), 8, device=dev, dtype=torch.float32)
+        for h, (w, b) in enumerate(zip(weights, biases)):
+            no = self.nout[h]
+            if no > 8 or w.reshape(no, -1).shape[1] != self.hid:
+                raise ValueError("HeadsSpec: heads of up to 8 outputs over the same hidden width")
+            stride = 2 if no <= 2 else 4 if no <= 4 else 8
+            m = torch.zeros(self.hid, stride, device=dev, dtype=torch.float32)
+            m[:, :no] = w.reshape(no, self.hid).t().float()
+            parts.append(m.reshape(-1))
+            self.b2[h, :no] = b.float()
+        self.w2 = torch.cat(parts).contiguous()
+        self.sig_mask = sum(1 << h for h, s in enumerate(sigmoid) if s)
+        self._nout_c = (ctypes.c_int * len(weights))(*self.nout)
+
+
+def conv_heads(spec, heads, x, outs):
+    """spec: ConvSpec of the stacked 3x3 head convolutions (Cin -> n_heads * hid, ReLU); heads: HeadsSpec;
+    outs: list of contiguous fp32 [B, nout_h, H, W] tensors.  One launch; fp32 mode only."""
+    arr = (ctypes.c_void_p * len(outs))(*[_lib.ptr(o) for o in outs])
+    _lib.call("sgta_planes_conv_heads", x.ref, _lib.ptr(spec.wpack), _lib.ptr(spec.scale), _lib.ptr(spec.shift),
+              _lib.ptr(heads.w2), _lib.ptr(heads.b2), arr, heads._nout_c, len(outs), heads.sig_mask, spec.Cin, heads.hid,
+              _lib.stream())
+
+
 def conv_sc(spec, x, y, epi, act=None):
     Ho = (x.H + 2 * spec.pad - spec.ksize) // spec.stride + 1
     Wo = (x.W + 2 * spec.pad - spec.ksize) // spec.stride + 1

@@ -340,3 +340,39 @@ def test_planes_upsample_and_tokens(ns):
             exp[b, ids[b, t].item()] = new[b, t]
     assert rel_err(after, exp) < (4e-3 if ns == 1 else 3e-7)
     assert float(big.view(0, B).to_nchw().abs().max()) == 0.0
+
+
+def test_conv_heads_fused_vs_two_stage_and_torch():
+    """sgta_planes_conv_heads (the 1x1 output convolutions of the heads in the epilogue of the stacked 3x3 head
+    convolution; base_model.py:121-135, :190-199, detector sigmoid sgta_detector.py:854-862) vs the two-stage planes
+    path it replaces and vs float64 torch, on a ragged map (the last M tile is partial) with three heads (7 / 2 / 2)."""
+    from sgtapose_b200 import planes as P
+    B, Cin, H, W, hid = 3, 64, 20, 28, 256
+    nouts, sig = [7, 2, 2], [True, False, False]
+    x = C.gen(301, B, Cin, H, W)
+    xb = _buf(x, 2)
+    xq = xb.to_nchw().cpu().double()
+    w0 = [C.gen(310 + h, hid, Cin, 3, 3) * 0.05 for h in range(3)]
+    b0 = [C.gen(320 + h, hid) * 0.1 for h in range(3)]
+    w2 = [C.gen(330 + h, nouts[h], hid, 1, 1) * 0.1 for h in range(3)]
+    b2 = [C.gen(340 + h, nouts[h]) * 0.1 for h in range(3)]
+    wm = torch.cat([P.weight_matrix(w.to(DEV)) for w in w0], 0)
+    bias0 = torch.cat(b0).to(DEV)
+    spec0 = P.ConvSpec(wm, torch.ones_like(bias0), bias0, Cin, 3, 1, 2, P.ACT_RELU)
+    heads = P.HeadsSpec([w.to(DEV) for w in w2], [b.to(DEV) for b in b2], sig)
+    outs = [torch.full((B, n, H, W), float("nan"), device=DEV) for n in nouts]
+    P.conv_heads(spec0, heads, xb.full, outs)
+    # two-stage planes path
+    hb = P.PlaneBuf(B, 3 * hid, H, W, 2, DEV)
+    P.conv(spec0, xb.full, hb.full)
+    for h in range(3):
+        ref = F.conv2d(F.relu(F.conv2d(xq, w0[h].double(), b0[h].double(), padding=1)), w2[h].double(), b2[h].double())
+        if sig[h]:
+            ref = torch.sigmoid(ref)
+        s2 = P.ConvSpec(P.weight_matrix(w2[h].to(DEV)), torch.ones(nouts[h], device=DEV), b2[h].to(DEV), hid, 1, 1, 2,
+                        P.ACT_SIGMOID if sig[h] else P.ACT_NONE, n_valid=nouts[h])
+        two = torch.zeros(B, nouts[h], H, W, device=DEV)
+        P.conv(s2, hb.view(c0=hid * h, C=hid), y_f32=two, epi=P.EPI_NCHW)
+        assert torch.isfinite(outs[h]).all()
+        assert rel_err(outs[h].cpu().double(), ref) < 2e-6, (h, rel_err(outs[h].cpu().double(), ref))
+        assert rel_err(outs[h].cpu(), two.cpu()) < 4e-6, (h, rel_err(outs[h].cpu(), two.cpu()))

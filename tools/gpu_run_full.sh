@@ -1,6 +1,6 @@
 # Round-end style validation on the GPU box: every GPU parity test, smoke(), the bench line, the reference arm.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "gpu tests rc=$?"; tail -4 gpurun_out/t_all.log
+timeout -k 10 900 python -m pytest tests -m gpu -x -q --timeout 150 > gpurun_out/t_all.log 2>&1; echo "gpu tests rc=$?"; tail -4 gpurun_out/t_all.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 ( time timeout 600 python bench.py > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err ) 2>&1 | grep real; echo "bench rc=$?"; cut -c1-400 gpurun_out/bench_fp32.json; tail -2 gpurun_out/bench_fp32.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_reference.json
