@@ -1111,7 +1111,8 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
   pdl_wait();
   const uint32_t tmem = *tmem_slot;
   const uint32_t acc_stride = (uint32_t)((p.acc_r + NS - 1) * NT);
-  const int total = p.m_tiles * p.n_tiles;
+  // tile2d (DCN, fp32 mode, n_tiles == 1): M tiles are blocks of 8 x 16 pixels (tile_row_m) instead of 128 consecutive rows
+  const int total = p.tile2d ? p.tiles_x * p.tiles_y * p.x.B : p.m_tiles * p.n_tiles;
   const int nkb = p.nkb;
 
   if (warp < G_PROD_WARPS) {
@@ -1154,7 +1155,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
         asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
         for (int e = tid; e < 9 * TM; e += G_PROD_WARPS * 32) {
           const int row = e & (TM - 1), tap = e >> 7;
-          const int m = m0 + row;
+          const int m = p.tile2d ? tile_row_m(p, t, row) : m0 + row;
           int px, py, b;
           decode_row(p, m, px, py, b);
           const bool ok = m < p.P && px >= 1 && px <= p.Wo && py >= 1 && py <= p.Ho;
@@ -1978,12 +1979,13 @@ static int launch_gather(ConvP& p, cudaStream_t st) {
   // (consuming G > 1 stages per issue group helps the MMA warp of the small-N layers but the
   // deeper ring it needs evicts the L1 the producers live on: measured slower, so G stays 1)
   if (SA > 3) SA = 3;                       // (DCN with 16 producer warps: 2 -> 3.17 ms, 3 -> 3.02 ms, 4 -> 3.06 ms per step)
+  // (2-D tiles with SA = 2, i.e. a 92 KB L1: within 2 % of SA = 3 on every DCN shape)
   if (SA < 2) { set_error("conv_gather: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
   p.SA = SA; p.SB = 0;
   const int smem = SA * stage + fixed + (p.b_resident ? p.nkb * b_bytes : 0);
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.tile2d ? p.tiles_x * p.tiles_y * p.x.B : p.m_tiles * p.n_tiles;
   const int grid = total < sms ? total : sms;
   if (NS == 2 && PROD == PROD_DCN && p.NT > 64) {
     constexpr int W = (NS == 2 && PROD == PROD_DCN) ? 1 : 0;     // (only this combination instantiates the WIDE variant)
@@ -2245,5 +2247,13 @@ extern "C" int sgta_planes_dcn(const sgta_planes* x, const void* offset_mask, co
   if (NS == 1 || (p.dbg & 256)) rc = NS == 2 ? try_launch_dcn_tile<2>(p, st) : try_launch_dcn_tile<1>(p, st);
   if (rc >= 0) return rc;
   p.tile2d = 0;
+  // fp32 mode: the __ldg gather over 2-D tiles.  A tile of 128 consecutive rows is a 1.3-row strip of a 96-wide map whose
+  // 9 x 4 corner reads span ~5 rows x 98 pixels x 256 B = 125 KB -- twice the L1 that the 190 KB operand ring leaves
+  // (ncu: L1 hit rate 48 %); an 8 x 16 block touches ~12 x 20 pixels = 61 KB.  Same per-pixel arithmetic in the same
+  // order: the outputs are bit-identical to the strip tiling (debug flag 524288 keeps that one).  Measured: 128 -> 64
+  // @48x48 157 -> 129 us, 128 -> 128 189 -> 155 us, 64 -> 64 @96x96 303 -> 294 us; DCN per step 3.10 -> 2.94 ms.
+  if (NS == 2 && p.n_tiles == 1 && p.Ho % 8 == 0 && p.Wo % 16 == 0 && !(p.dbg & 524288)) {
+    p.tile2d = 1; p.tiles_x = p.Wo / 16; p.tiles_y = p.Ho / 8;
+  }
   return NS == 2 ? launch_gather<PROD_DCN, 2>(p, st) : launch_gather<PROD_DCN, 1>(p, st);
 }
