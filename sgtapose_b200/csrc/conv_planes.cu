@@ -1150,11 +1150,15 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
         // XORs its own group index) and the four mask*bilinear weights; every lane of a row reads
         // them back (broadcast).  The producers are instruction-bound (tools/dcn_bench.py: the same
         // time with the global loads removed), so everything row-invariant lives here.
+        // A warp only ever reads the entries of ITS OWN 4 * RPL rows, so it builds exactly those (9 taps x 4 * RPL rows)
+        // and nothing but __syncwarp orders the table: the 512 producers no longer meet at two CTA-wide barriers per
+        // tile (ncu source page: 15 % of the kernel's stall samples sat on them) and drift as far as the ring allows.
         uint4* tab_o = reinterpret_cast<uint4*>(tab);
         float4* tab_w = reinterpret_cast<float4*>(tab + 9 * TM * 16);
-        asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
-        for (int e = tid; e < 9 * TM; e += G_PROD_WARPS * 32) {
-          const int row = e & (TM - 1), tap = e >> 7;
+        __syncwarp();
+        for (int e2 = lane; e2 < 9 * 4 * RPL; e2 += 32) {
+          const int tap = e2 / (4 * RPL), row = warp * (4 * RPL) + (e2 - tap * (4 * RPL));
+          const int e = tap * TM + row;
           const int m = p.tile2d ? tile_row_m(p, t, row) : m0 + row;
           int px, py, b;
           decode_row(p, m, px, py, b);
@@ -1180,7 +1184,7 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
                                 (r2 << 7) | ((r2 & 7u) << 4), (r3 << 7) | ((r3 & 7u) << 4));
           tab_w[e] = make_float4(msk * hy * hx, msk * hy * lx, msk * ly * hx, msk * ly * lx);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
+        __syncwarp();
         const uint32_t gx = (uint32_t)c8 << 4;
         const uint32_t tab_s = smem_u32(tab);
         for (int kc = 0; kc < p.KC; ++kc) {
