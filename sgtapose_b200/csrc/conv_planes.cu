@@ -1345,11 +1345,11 @@ __global__ void __launch_bounds__(GThreads<PROD>::value, 1) conv_gather_kernel(c
         if (++lkb == nkb) { lkb = 0; lt += gridDim.x; }
       };
       auto store_block = [&](const uint4 (&src)[RPL][NS]) {
-        unsigned char* sA = wait_stage();
+        const uint32_t sA = smem_u32(wait_stage());           // explicit STS (a generic pointer compiles to ST.E)
 #pragma unroll
         for (int i = 0; i < RPL; ++i)
 #pragma unroll
-          for (int pl = 0; pl < NS; ++pl) *reinterpret_cast<uint4*>(sA + pl * a_plane + soff[i]) = src[i][pl];
+          for (int pl = 0; pl < NS; ++pl) sts128(sA + pl * a_plane + soff[i], src[i][pl]);
         publish();
       };
       if (p.dbg & 1) {
@@ -1602,8 +1602,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
           // bit 31 of .x flags a sample outside the staged window: .x then holds the global row of corner 0
           uint4* tab_o = reinterpret_cast<uint4*>(tab);
           float4* tab_w = reinterpret_cast<float4*>(tab + 9 * TM * 16);
-          for (int e = tid; e < 9 * TM; e += D_PROD_WARPS * 32) {
-            const int row = e & (TM - 1), tap = e >> 7;
+          // (a warp builds the entries of its own 4 * RPL rows -- the only ones it reads: no CTA barrier after the build)
+          for (int e2 = lane; e2 < 9 * 4 * RPL; e2 += 32) {
+            const int tap = e2 / (4 * RPL), row = warp * (4 * RPL) + (e2 - tap * (4 * RPL));
+            const int e = tap * TM + row;
             const int py = y0 + (row >> 4) + 1, px = x0 + (row & 15) + 1;       // padded coordinates
             const float* om = p.om + ((size_t)((long long)b * Hp + py) * Wp + px) * 32;
             const float dy = __ldg(om + 2 * tap), dx = __ldg(om + 2 * tap + 1), ml = __ldg(om + 18 + tap);
@@ -1632,7 +1634,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) dcn_tile_kernel(const __grid_con
             tab_w[e] = make_float4(msk * hy * hx, msk * hy * lx_, msk * ly_ * hx, msk * ly_ * lx_);
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(D_PROD_WARPS * 32) : "memory");
+        __syncwarp();
         mbar_wait(xbar, xph);
         xph ^= 1u;
         const unsigned char* xk = p.x.base + (((size_t)(p.x.chunk0 + kc) * p.x.rows) << 7);
@@ -1984,6 +1986,7 @@ static int launch_gather(ConvP& p, cudaStream_t st) {
   // deeper ring it needs evicts the L1 the producers live on: measured slower, so G stays 1)
   if (SA > 3) SA = 3;                       // (DCN with 16 producer warps: 2 -> 3.17 ms, 3 -> 3.02 ms, 4 -> 3.06 ms per step)
   // (2-D tiles with SA = 2, i.e. a 92 KB L1: within 2 % of SA = 3 on every DCN shape)
+  if (PROD == PROD_DCN && (p.dbg >> 20) & 7) { const int want = (p.dbg >> 20) & 7; if (want >= 2 && want <= avail / stage) SA = want; }   // experiments
   if (SA < 2) { set_error("conv_gather: tile does not fit shared memory"); return SGTA_EUNSUPPORTED; }
   p.SA = SA; p.SB = 0;
   const int smem = SA * stage + fixed + (p.b_resident ? p.nkb * b_bytes : 0);
