@@ -525,7 +525,8 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
 
 // the batch-looping kernels serve LARGE pos_embed blocks (level 0: 44.8 MB re-read per sample otherwise)
 static bool big_pos_case(const float* pos, int B, int heads, int nq, int nk) {
-  return pos != nullptr && (size_t)heads * nq * nk * sizeof(float) > (16u << 20) && B >= 4;
+  static const size_t thr_mb = getenv("SGTA_ATTN_POS_MB") ? (size_t)atoi(getenv("SGTA_ATTN_POS_MB")) : 16;
+  return pos != nullptr && (size_t)heads * nq * nk * sizeof(float) > (thr_mb << 20) && B >= 4;
 }
 static size_t rows_kernel_smem(int nk, int D) {
   const int nk_pad = nk + ((33 - (nk & 31)) & 31);
