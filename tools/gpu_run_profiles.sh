@@ -8,6 +8,6 @@ for mode in fp32 bf16; do
   timeout -k 5 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv --log-file gpurun_out/launches_$mode.csv python bench.py --mode $mode --profile-pass --no-cpu-baseline > gpurun_out/launches.log 2>&1
   python tools/launch_summary.py gpurun_out/launches_$mode.csv 150 > gpurun_out/launch_summary_$mode.txt 2>&1
 done
-SKIP=45 timeout -k 10 300 bash tools/ncu_capture.sh heads "conv_shift_kernel" 1 1 > /dev/null 2>&1
+SKIP=46 timeout -k 10 300 bash tools/ncu_capture.sh heads "conv_shift_kernel" 1 1 > /dev/null 2>&1
 tail -2 gpurun_out/heads_ncu.log
 ls -la gpurun_out | grep "dcn_\|launch\|heads_"
