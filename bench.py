@@ -328,7 +328,7 @@ def run_ours(args):
                    "skip_dead_levels": bool(args.skip_dead_levels),
                    "engine": "eager modules + libsgta_b200" if args.engine == "eager" else
                              "InferenceEngine (NHWC, tcgen05 convs, CUDA graph)",
-                   "arithmetic": "fp32 activations as fp16 hi+lo planes, 3 tensor-core MMAs per K step, rotating fp32 accumulators"
+                   "arithmetic": "fp32 activations as fp16 hi+lo planes, 3 tensor-core MMAs per K step (2 for N tiles <= 64), band-drained fp32 accumulators"
                                  if args.mode == "fp32" else "bf16 activations and MMAs, fp32 accumulate"},
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
