@@ -163,10 +163,10 @@ pl_upsample_add_kernel(View x, const float* __restrict__ w, View skip, int has_s
 // loads and of the address arithmetic of the general kernel.  Measured: 0.530 -> 0.519 ms over the 8 launches of a
 // step only -- the kernel is bound by memory latency (ncu: DRAM 32 %, L1 42 %, issue 55 %), not by instructions.
 // Same tap order per output as the general kernel: skip, then (i, j), (i, j-1), (i-1, j), (i-1, j-1).
-constexpr int UP2_ROWS = 4;            // input rows per CTA
+constexpr int UP2_ROWS = 2;            // input rows per CTA
 template <int NS>
-__global__ void __launch_bounds__(256)
-pl_upsample2_add_kernel(View x, const float* __restrict__ w, View skip, int has_skip, View y, int C) {
+__global__ void __launch_bounds__(256, 2)
+pl_upsample2_add_kernel(View x, const float* __restrict__ w, View skip, int has_skip, View y, int C, int rows) {
   extern __shared__ __align__(16) float ups_w[];
   pdl_trigger();
   for (int i = threadIdx.x; i < 16 * C; i += 256) {
@@ -180,24 +180,49 @@ pl_upsample2_add_kernel(View x, const float* __restrict__ w, View skip, int has_
   if (t >= (x.W + 1) * G) return;
   const int j = t / G, g = t - j * G;
   const int b = blockIdx.z;
-  const int i1 = min((int)(blockIdx.y + 1) * UP2_ROWS, x.H + 1);
-  for (int i = blockIdx.y * UP2_ROWS; i < i1; ++i) {
+  const int i1 = min((int)(blockIdx.y + 1) * rows, x.H + 1);
+  const int chunk = g >> 3, c8 = g & 7;            // PL views: 64-channel chunk and 16-byte group of this thread's 8 channels
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int i = blockIdx.y * rows; i < i1; ++i) {
+    // all 16 loads of the iteration (4 inputs + 4 skips, per plane) are issued before anything waits on them: the
+    // per-output load -> wait -> FMA -> store chain made the kernel latency-bound (2 waves of ~20 us CTAs)
+    uint4 xi[2][2][NS], sk[2][2][NS];
+    long long po[2][2];
+    bool ok[2][2];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long pi = frame_row(x, b, i - 1 + dy, j - 1 + dx);
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2)
+          xi[dy][dx][s2] = __ldg(reinterpret_cast<const uint4*>(x.base + pl_offset(x, s2, chunk, pi, c8)));
+      }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int oy = 2 * i - 1 + a, ox = 2 * j - 1 + bb;
+        ok[a][bb] = oy >= 0 && oy < y.H && ox >= 0 && ox < y.W;
+        po[a][bb] = frame_row(y, b, oy, ox);
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2)
+          sk[a][bb][s2] = (has_skip && ok[a][bb])
+                              ? __ldg(reinterpret_cast<const uint4*>(skip.base + pl_offset(skip, s2, chunk, po[a][bb], c8)))
+                              : zero4;
+      }
     float v[2][2][8];
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) load8<NS>(x, frame_row(x, b, i - 1 + dy, j - 1 + dx), g * 8, v[dy][dx]);
+      for (int dx = 0; dx < 2; ++dx) decode8<NS>(xi[dy][dx][0], xi[dy][dx][NS - 1], v[dy][dx]);
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
-      const int oy = 2 * i - 1 + a;
-      if (oy < 0 || oy >= y.H) continue;
 #pragma unroll
       for (int bb = 0; bb < 2; ++bb) {
-        const int ox = 2 * j - 1 + bb;
-        if (ox < 0 || ox >= y.W) continue;
+        if (!ok[a][bb]) continue;
         float acc[8];
-        const long long po = frame_row(y, b, oy, ox);
-        if (has_skip) load8<NS>(skip, po, g * 8, acc);
+        if (has_skip) decode8<NS>(sk[a][bb][0], sk[a][bb][NS - 1], acc);
         else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[c] = 0.f;
@@ -215,7 +240,7 @@ pl_upsample2_add_kernel(View x, const float* __restrict__ w, View skip, int has_
             acc[4] = fmaf(u[4], w1.x, acc[4]); acc[5] = fmaf(u[5], w1.y, acc[5]);
             acc[6] = fmaf(u[6], w1.z, acc[6]); acc[7] = fmaf(u[7], w1.w, acc[7]);
           }
-        store8<NS>(y, po, g * 8, acc);
+        pl_store8<NS>(y, chunk, po[a][bb], c8, acc);
       }
     }
   }
@@ -377,10 +402,12 @@ extern "C" int sgta_planes_upsample_add(const sgta_planes* x, const void* w_up, 
   View vx = make_view(x), vy = make_view(y), vs = make_view(skip);
   const size_t smem = sizeof(float) * 4 * f * f * C;
   SGTA_REQUIRE(smem <= 96 * 1024 && y->B <= 65535, "sgta_planes_upsample_add: kernel %dx%d x %d channels too large", 2 * f, 2 * f, C);
-  if (f == 2 && !(debug_flags() & 65536)) {
-    dim3 grid2(cdiv((long long)(x->W + 1) * (C / 8), 256), cdiv(x->H + 1, UP2_ROWS), y->B);
+  if (f == 2 && !(debug_flags() & 65536) && x->layout == SGTA_LAYOUT_PL && y->layout == SGTA_LAYOUT_PL &&
+      (!skip || skip->layout == SGTA_LAYOUT_PL)) {
+    static const int rows = getenv("SGTA_UP2_ROWS") ? atoi(getenv("SGTA_UP2_ROWS")) : UP2_ROWS;
+    dim3 grid2(cdiv((long long)(x->W + 1) * (C / 8), 256), cdiv(x->H + 1, rows), y->B);
     NS_DISPATCH(x->nplanes, {
-      launch_k(pl_upsample2_add_kernel<NS>, grid2, 256, sizeof(float) * 16 * C, (cudaStream_t)stream, vx, (const float*)w_up, vs, (int)(skip != nullptr), vy, C);
+      launch_k(pl_upsample2_add_kernel<NS>, grid2, 256, sizeof(float) * 16 * C, (cudaStream_t)stream, vx, (const float*)w_up, vs, (int)(skip != nullptr), vy, C, rows);
     });
     return check_launch("pl_upsample2_add_kernel");
   }
