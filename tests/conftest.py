@@ -23,9 +23,14 @@ def pytest_collection_modifyitems(config, items):
     from oracle import ref_import
     has_gpu = torch.cuda.is_available()
     has_ref = ref_import.reference_available()
+    has_timeout = config.pluginmanager.hasplugin("timeout")
     for it in items:
         if "gpu" in it.keywords and not has_gpu:
             it.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "gpu" in it.keywords and has_timeout and it.get_closest_marker("timeout") is None:
+            # a deadlocked kernel must fail its test, not hang the run: watchdog thread (works while the main thread
+            # sits in a CUDA synchronise), generous limit -- the whole GPU suite takes ~25 s
+            it.add_marker(pytest.mark.timeout(600, method="thread"))
         if "reference" in it.keywords and not has_ref:
             it.add_marker(pytest.mark.skip(reason="/root/reference not present"))
 
