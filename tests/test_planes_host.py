@@ -82,3 +82,29 @@ def test_stem_superpixel_matrix_vs_conv2d():
                 out = wm @ a
                 for j in range(4):
                     assert torch.allclose(out[32 * j:32 * j + 32], ref[b, :, y, 4 * X + j], atol=1e-5)     # the matrix is built in fp32
+
+
+def test_heads_spec_packing_is_the_1x1_convolutions():
+    """HeadsSpec (host half of sgta_planes_conv_heads; base_model.py:121-135): the packed rows [hid][stride] + biases
+    [n_heads][8] reproduce the three 1x1 output convolutions when applied the way the kernel's epilogue applies them
+    (out[o] = sum_k hidden[k] * w2[k][o] + b2[o]), strides 8 / 2 / 2 for 7 / 2 / 2 outputs, zero padding elsewhere."""
+    import torch.nn.functional as F
+    from sgtapose_b200 import planes as P
+    torch.manual_seed(3)
+    hid, nouts = 256, [7, 2, 2]
+    ws = [torch.randn(n, hid, 1, 1) for n in nouts]
+    bs = [torch.randn(n) for n in nouts]
+    hs = P.HeadsSpec(ws, bs, [True, False, False])
+    assert hs.nout == nouts and hs.hid == hid and hs.sig_mask == 1
+    strides = [8, 2, 2]
+    assert hs.w2.numel() == hid * sum(strides) and tuple(hs.b2.shape) == (3, 8)
+    hidden = torch.relu(torch.randn(5, 3 * hid, 4, 6))
+    off = 0
+    for h, (n, st) in enumerate(zip(nouts, strides)):
+        m = hs.w2[off:off + hid * st].view(hid, st)
+        off += hid * st
+        assert torch.count_nonzero(m[:, n:]) == 0 and torch.count_nonzero(hs.b2[h, n:]) == 0
+        x = hidden[:, h * hid:(h + 1) * hid]
+        got = torch.einsum("bkyx,ko->boyx", x.double(), m[:, :n].double()) + hs.b2[h, :n].double().view(1, n, 1, 1)
+        ref = F.conv2d(x.double(), ws[h].double(), bs[h].double())
+        assert torch.allclose(got, ref, rtol=1e-12, atol=1e-12)
