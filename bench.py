@@ -230,7 +230,6 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = step_launches * args.steps
-    clocks = sampler.stop() if rank == 0 else None
     if rank == 0 and args.engine != "eager":
         timed_heads = {k: v.clone() for k, v in eng.out.items()}       # heads + decoded results of the LAST TIMED step
         timed_dets = {k: dets[k].clone() for k in ("xs", "ys", "inds", "scores")}
@@ -266,6 +265,7 @@ def run_ours(args):
         barrier()
         d2h = sum(v.numel() * v.element_size() for v in res.values())
     ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over BOTH timed regions (value and e2e)
 
     # per-kernel timing of the DCN launches (CUDA events on the launching stream)
     dcn_ms = time_dcn_kernels(eager_pass)
