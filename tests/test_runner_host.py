@@ -116,3 +116,20 @@ def test_runner_gloo_world2_matches_single_rank():
         assert np.array_equal(k, kps), rank
         assert np.array_equal(p_, pose), rank
         assert np.array_equal(s_[:, 0, 0], np.arange(n_clips) + 0.5), rank
+
+
+def test_runner_edge_cases_empty_shard_and_single_frame():
+    """No clips at all (an idle rank keeps its place in the collective with an empty shard) and one-frame clips
+    (every pose comes from `solve_poses`, none from a next frame's `begin`)."""
+    from sgtapose_b200.runner import SequenceRunner
+    r = SequenceRunner([_Det(2), _Det(2)])
+    out = r.run(0, 3, _images, _x3d)
+    assert out["kps_raw"].shape == (0, 3, 7, 2) and out["pose"].shape == (0, 3, 7) and out["scores"].shape == (0, 3, 7)
+    assert r.timing["waves"] == 0
+    out = r.run(3, 1, _images, _x3d)
+    kps, pose = _expected(3, 1)
+    assert np.array_equal(out["kps_raw"], kps) and np.array_equal(out["pose"], pose)
+    # a rank beyond the clip count owns nothing and must not touch its detectors
+    r2 = SequenceRunner([_Det(2)], world=4, rank=3)
+    out = r2.run(2, 2, _images, _x3d, gather=False)
+    assert out["kps_raw"].shape[0] == 0 and r2.timing["local_clips"] == 0

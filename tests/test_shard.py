@@ -3,6 +3,7 @@ multi-GPU path (sgtapose_b200/shard.py)."""
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -36,14 +37,15 @@ def _worker(rank, world, port, n_clips, q):
         dist.destroy_process_group()
 
 
-def test_gather_results_gloo_world2():
+@pytest.mark.parametrize("n_clips", [5, 1])               # ragged 3 + 2; one clip: rank 1 owns nothing
+def test_gather_results_gloo_world2(n_clips):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    n_clips, world = 5, 2                                  # ragged: 3 + 2 clips
+    world = 2
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_clips, q)) for r in range(world)]
     for p in procs:
         p.start()
