@@ -358,3 +358,43 @@ def test_oracle_pnp_front_end_vs_reference_golden(golden):
         a, b = odet.is_pnp(prev[good], kps[good], nxt, kps, C.CAMERA_K)
         assert np.array_equal(a, g["prev_%d" % i])
         assert np.allclose(b, g["next_%d" % i], rtol=0, atol=1e-9), i
+
+
+@pytest.mark.reference
+def test_oracle_decode_vs_live_reference_random_maps():
+    """The oracle's live decode against the UNMODIFIED reference `dream_generic_decode` (decode.py:184-313 ->
+    utils.py:207-284 -> image_proc.py:1032-1143) on freshly seeded maps that are NOT in the golden set: 0-3 blobs per
+    channel with random centres (borders included), widths and amplitudes over a noise floor.  `.cuda()` inside the
+    reference decode is patched to the identity for the call (no GPU here), as in oracle/make_golden.py."""
+    ns = ref_import.load_reference()
+    opt = ref_import.default_opt()
+    rng = np.random.default_rng(20241)
+    N = 12
+    yy, xx = np.mgrid[0:96, 0:96].astype(np.float32)
+    hms = (rng.random((N, 7, 96, 96), dtype=np.float32) * 0.005).astype(np.float32)
+    for n in range(N):
+        for c in range(7):
+            for _ in range(int(rng.integers(0, 4))):
+                cx, cy = rng.uniform(-1, 96, 2)
+                s2 = rng.uniform(1.0, 9.0)
+                hms[n, c] = np.maximum(hms[n, c], (rng.uniform(0.05, 1.0) *
+                                                   np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s2))).astype(np.float32))
+    reg = (rng.standard_normal((N, 2, 96, 96)) * 0.3).astype(np.float32)
+    trk = (rng.standard_normal((N, 2, 96, 96)) * 2.0).astype(np.float32)
+    d = odec.dream_generic_decode(hms, reg, trk)
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        found = 0
+        for n in range(N):
+            o = {"hm": torch.from_numpy(hms[n:n + 1]), "reg": torch.from_numpy(reg[n:n + 1]),
+                 "tracking": torch.from_numpy(trk[n:n + 1])}
+            r = ns.decode.dream_generic_decode(o, K=7, opt=opt)
+            for k in ("xs", "ys", "cts", "scores", "clses", "tracking"):
+                assert np.array_equal(d[k][n:n + 1], r[k].numpy()), (k, n)
+            for k in ("cts_wreg", "regs"):
+                np.testing.assert_allclose(d[k][n:n + 1], r[k].numpy(), rtol=0, atol=1e-6)
+            found += int((r["scores"].numpy() > 0).sum())
+    finally:
+        torch.Tensor.cuda = saved
+    assert 20 < found < 7 * N                             # both outcomes (a detection / missing or ambiguous) occur
