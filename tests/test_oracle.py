@@ -398,3 +398,60 @@ def test_oracle_decode_vs_live_reference_random_maps():
     finally:
         torch.Tensor.cuda = saved
     assert 20 < found < 7 * N                             # both outcomes (a detection / missing or ambiguous) occur
+
+
+@pytest.mark.reference
+def test_oracle_priors_vs_live_reference_random_keypoints():
+    """oracle/priors.py and the product's host affine / clip helpers against the UNMODIFIED reference
+    sgtapose/utilities.py (:800-853, :889-972, :1045-1098) on 60 freshly seeded keypoint sets per size that are not in
+    the golden file (points inside, outside and on the edges of the raw frame): bit-exact."""
+    from oracle import priors as OP
+    from oracle.make_golden_priors import load_utilities
+    from sgtapose_b200 import priors as PP
+    U = load_utilities()
+    rng = np.random.default_rng(9917)
+    c = np.array([320.0, 180.0], dtype=np.float32)
+    for S in (384, 128, 480):
+        q = S // 4
+        t_in, t_out = U.get_affine_transform(c, 640.0, 0, [S, S]), U.get_affine_transform(c, 640.0, 0, [q, q])
+        assert np.array_equal(OP.get_affine_transform(c, 640.0, [S, S]), t_in)
+        assert np.array_equal(PP.get_affine_transform(c, 640.0, 0, [q, q]), t_out)
+        for _ in range(60):
+            kp = rng.uniform([-30, -30], [670, 390], size=(7, 2))
+            kp[rng.integers(0, 7)] = np.round(kp[rng.integers(0, 7)])             # some exactly on raw pixel centres
+            for t, w in ((t_in, S), (t_out, q)):
+                want = U.affine_transform_and_clip(kp, t, w, w, 640, 360)
+                assert np.array_equal(OP.affine_transform_and_clip(kp, t, w, w, 640, 360), want)
+                assert np.array_equal(PP.affine_transform_and_clip(kp[None], t, w, w, 640, 360)[0], want)
+            assert np.array_equal(OP.get_prev_hm_wo_noise(kp, t_in, S, S, 640, 360),
+                                  U.get_prev_hm_wo_noise(kp, t_in, S, S, 640, 360))
+            assert np.array_equal(OP.get_prev_hm_wo_noise_cls(kp, 7, t_out, q, q, 640, 360),
+                                  U.get_prev_hm_wo_noise_cls(kp, kp, t_out, q, q, 640, 360))
+
+
+@pytest.mark.reference
+def test_oracle_token_index_vs_live_reference_random_priors():
+    """oracle/model.py::topk_index / window_ids / gather_tokens against the UNMODIFIED reference `get_topk_index` and
+    `get_topk_features_scale` (dla.py:898-968) on seeded prior maps with unique maxima anywhere in the 96 x 96 map
+    (corners and edges included), at all six pyramid levels -- the fp32 index detour of SURVEY.md H4 must come out
+    the same for every position, not only for the pinned (47,47) -> 1151 case."""
+    ns = ref_import.load_reference()
+    rng = np.random.default_rng(4711)
+    B = 6
+    pm = (rng.random((B, 7, 96, 96), dtype=np.float32) * 0.5).astype(np.float32)
+    pos = [(0, 0), (95, 95), (0, 95), (95, 0), (47, 47), (48, 1), (1, 94)]
+    for b in range(B):
+        for c in range(7):
+            x, y = pos[c] if b == 0 else (int(v) for v in rng.integers(0, 96, 2))
+            pm[b, c, y, x] = 1.0                                                   # unique maximum (H5: no ties)
+    pm = torch.from_numpy(pm)
+    ref_xy, _ = ns.dla.get_topk_index(pm, pm, 1)
+    xy = omodel.topk_index(pm, 1)
+    assert torch.equal(xy, ref_xy)
+    sizes, kernels = [384, 192, 96, 48, 24, 12], [12, 6, 3, 1, 1, 1]
+    for lvl in range(6):
+        feats = torch.from_numpy(rng.standard_normal((B, 3, sizes[lvl], sizes[lvl])).astype(np.float32))
+        rows, _, fid = ns.dla.get_topk_features_scale(feats, ref_xy, scale_num=omodel.SCALE_LIST[lvl], kernel=kernels[lvl])
+        mine = omodel.window_ids(xy, omodel.SCALE_LIST[lvl], kernels[lvl], sizes[lvl], sizes[lvl])
+        assert torch.equal(mine, fid), lvl
+        assert torch.equal(omodel.gather_tokens(feats, mine), rows), lvl
